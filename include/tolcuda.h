@@ -1,0 +1,136 @@
+/* libtolcuda -- B200 (sm_100a) evaluator for tol's SNOPT user function (F and sparse G).
+ *
+ * C ABI: plain pointers and sizes only.  Every entry point names the reference interface it
+ * replaces (file:line into lingaqing/tol).  All functions return 0 on success, a positive
+ * cudaError_t value on a CUDA failure, or a negative TOLCUDA_E* code; none throws across the ABI.
+ * tolcuda_last_error() returns a human-readable message for the calling thread's last failure.
+ *
+ * There is NO CPU fallback: every evaluation runs the sm_100a kernels in fg_kernels.cu. */
+#ifndef TOLCUDA_H_
+#define TOLCUDA_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* formulations: reference src/tol.cpp:5-36 (mission_select) */
+#define TOLCUDA_G7 7   /* guidance, reference src/problemG7.cpp */
+#define TOLCUDA_S10 10 /* loiter,   reference src/problemS10.cpp */
+
+/* wind models: reference src/problem.cpp:475-531 (modelWind cases 0 and 1; case 1 is what the
+ * reference runs whenever its MongoDB wind server is unreachable, src/problem.cpp:63-78) */
+#define TOLCUDA_WIND_NONE 0
+#define TOLCUDA_WIND_LINEAR_LAYER 1
+
+/* error codes (negative; positive values are cudaError_t) */
+#define TOLCUDA_EINVAL (-1)      /* bad argument                                         */
+#define TOLCUDA_EUNSUPPORTED (-2) /* formulation / wind model / ts outside what is built */
+#define TOLCUDA_ENOCTX (-3)      /* DEFINEGusrfg_ called with no bound context            */
+#define TOLCUDA_EIO (-4)         /* .param file missing or malformed                      */
+#define TOLCUDA_ENOMEM (-5)
+
+/* flags for tolcuda_eval_batch */
+#define TOLCUDA_NEED_F 0x1
+#define TOLCUDA_NEED_G 0x2
+#define TOLCUDA_HOST_PTRS 0x10   /* x/F/G are host memory (staged through pinned buffers)  */
+#define TOLCUDA_DEVICE_PTRS 0x20 /* x/F/G are device memory on the context's device        */
+/* neither pointer flag: detected with cudaPointerGetAttributes on x */
+#define TOLCUDA_NO_SYNC 0x40 /* device pointers only: return after enqueueing on the context's
+                                stream instead of synchronising it                         */
+
+typedef struct tolcuda_ctx *tolcuda_handle;
+
+/* What reference `problem::problem(arguments&)` gathers before the first callback
+ * (src/problem.cpp:13-60, src/parameters.cpp:42-148):
+ *   aircraft[15] = mm,b,SS,ee,AR,Cd0,CLmin,CLmax,phimax,Vamin,Vamax,gammamax,phidotmax,Tmin,Tmax
+ *                  (file order, angles already in radians); the path uses mm,SS,ee,AR,Cd0
+ *   gains[5]     = kT,kp,kv,ka,kdt
+ *   goal[4]      = xg,yg,zg,rg in NED (xg = north_goal, yg = east_goal, zg = -up_goal;
+ *                  src/problem.cpp:24-27)
+ *   numbounds is implied by the formulation (12 for G7, 11 for S10; problems/<M>/snopt.param). */
+typedef struct tolcuda_config {
+    int formulation; /* TOLCUDA_G7 | TOLCUDA_S10 */
+    int ts;          /* time segments ("N nodes"), >= 1 */
+    int wind_model;  /* TOLCUDA_WIND_* */
+    int device;      /* CUDA device ordinal */
+    double aircraft[15];
+    double gains[5];
+    double goal[4];
+} tolcuda_config;
+
+/* Replaces the problemG7 / problemS10 construction in reference src/tol.cpp:5-36 for the
+ * evaluation path: builds the sparsity pattern once (closed form of countG, src/problem.cpp:813-919),
+ * uploads the constants to __constant__ memory, creates the stream and pinned staging buffers. */
+int tolcuda_create(const tolcuda_config *cfg, tolcuda_handle *out);
+
+/* Same, reading the reference's own files: <root>aircraft/<aircraft>.param,
+ * <root>problems/<mission>/{gains,snopt}.param (reference src/parameters.cpp:42-148; root must end
+ * in '/').  east/north/up and the goal are the reference CLI's positional arguments
+ * (src/arguments.cpp:32-46).  ts_override > 0 replaces the ts of snopt.param. */
+int tolcuda_create_from_files(const char *root, const char *aircraft, const char *mission,
+                              double east, double north, double up, double east_goal,
+                              double north_goal, double up_goal, double radius_goal,
+                              int ts_override, int device, tolcuda_handle *out);
+
+int tolcuda_destroy(tolcuda_handle h);
+
+/* n, neF, neG as reference src/problem.cpp:151-152 and countG's final neG */
+int tolcuda_dims(tolcuda_handle h, int *n, int *neF, int *neG);
+
+/* iGfun/jGvar exactly as reference countG leaves them for snoptProblemA::setG
+ * (src/problem.cpp:870-871, :1230): 0-based, sorted by row then column, neG entries each. */
+int tolcuda_pattern(tolcuda_handle h, int *iGfun, int *jGvar);
+
+/* The same two queries without a context (and without touching CUDA), for a driver that must size
+ * and fill SNOPT's arrays before any device exists: closed form of reference countG
+ * (src/problem.cpp:813-919) -- neG = 105*ts+48 (G7), 107*ts+37 (S10). */
+int tolcuda_problem_dims(int formulation, int ts, int *n, int *neF, int *neG);
+int tolcuda_problem_pattern(int formulation, int ts, int *iGfun, int *jGvar);
+
+/* One trajectory, host pointers: what reference DEFINEGusrfg_ computes (src/DefineFG.cpp:24-38)
+ * without the debug dumps.  Writes F[0..neF) if needF > 0 and G[0..neG) if needG > 0. */
+int tolcuda_eval(tolcuda_handle h, const double *x, int needF, double *F, int needG, double *G);
+
+/* B independent trajectories in one launch, trajectory-major: trajectory b reads x + b*ldx
+ * (n doubles) and writes F + b*ldF (neF doubles) and G + b*ldG (neG doubles, coordinate order of
+ * tolcuda_pattern).  Leading dimensions are in doubles; padding them to a multiple of 16 keeps
+ * every trajectory 128-byte aligned (tolcuda_padded_ld).  flags: TOLCUDA_NEED_* | pointer kind. */
+int tolcuda_eval_batch(tolcuda_handle h, int B, const double *x, long ldx, double *F, long ldF,
+                       double *G, long ldG, int flags);
+
+/* smallest multiple of 16 doubles (128 bytes) that holds `len` doubles */
+long tolcuda_padded_ld(long len);
+
+/* run the context's work on a caller-owned cudaStream_t (e.g. torch's current stream) so that the
+ * caller's CUDA events bracket the kernels; NULL restores the context's own stream */
+int tolcuda_set_stream(tolcuda_handle h, void *cuda_stream);
+int tolcuda_synchronize(tolcuda_handle h);
+
+/* number of kernel launches this context has issued (bench.py's gpu_launches) */
+long tolcuda_launch_count(tolcuda_handle h);
+
+/* Makes `h` the process-global context DEFINEGusrfg_ evaluates with, as reference `problem *prob`
+ * (src/tol.cpp:3, include/global_objects.h:5) is for the reference callback.  NULL unbinds. */
+int tolcuda_bind_global(tolcuda_handle h);
+
+/* The snOptA user function, signature of snFunA (reference include/snopt/snopt.h:60-66), symbol and
+ * argument meaning of reference include/DefineFG.h:5-17 / src/DefineFG.cpp:9-48, so
+ * `setUserFun(DEFINEGusrfg_)` (src/problem.cpp:1234) binds it unchanged.  Success leaves *Status
+ * untouched (the reference never writes it); a CUDA failure or a missing context sets *Status = -2
+ * (SNOPT: terminate) and reports on stderr.  cu/iu/ru are ignored as in the reference. */
+void DEFINEGusrfg_(int *Status, int *n, double x[], int *needF, int *neF, double F[], int *needG,
+                   int *neG, double G[], char *cu, int *lencu, int iu[], int *leniu, double ru[],
+                   int *lenru);
+
+/* reference parameters::readparams (src/parameters.cpp:14-34): one leading number per line, text
+ * from the first '/' on ignored, lines that do not start with a number skipped.  Stores up to
+ * `cap` values and returns the number found in *count. */
+int tolcuda_read_params(const char *path, double *values, int cap, int *count);
+
+const char *tolcuda_last_error(void);
+const char *tolcuda_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOLCUDA_H_ */

@@ -52,22 +52,29 @@ def _ip(a):
     return a.ctypes.data_as(C.POINTER(C.c_int))
 
 
-def make_root(ts=None, mission=None, src=REF_PARAMS):
+def make_root(ts=None, mission=None, gains=None, src=REF_PARAMS):
     """Return (root_path_with_trailing_slash, tmpdir_or_None).  ts != shipped value needs a private
     copy of the .param tree with line 2 of problems/<mission>/snopt.param edited (the reference
-    reads ts only from that file, reference src/parameters.cpp:130-148)."""
-    if ts is None:
+    reads ts only from that file, reference src/parameters.cpp:130-148); `gains` (kT,kp,kv,ka,kdt)
+    likewise rewrites problems/<mission>/gains.param."""
+    if ts is None and gains is None:
         return src.rstrip("/") + "/", None
     tmp = tempfile.mkdtemp(prefix="tolref_params_")
     for d in ("aircraft", "problems"):
         shutil.copytree(os.path.join(src, d), os.path.join(tmp, d))
-    p = os.path.join(tmp, "problems", mission, "snopt.param")
-    os.chmod(p, 0o644)
-    with open(p, "r", newline="") as fh:
-        lines = fh.read().split("\n")
-    lines[1] = "%d       // Number of time segments  " % ts
-    with open(p, "w", newline="") as fh:
-        fh.write("\n".join(lines))
+    if ts is not None:
+        p = os.path.join(tmp, "problems", mission, "snopt.param")
+        os.chmod(p, 0o644)
+        with open(p, "r", newline="") as fh:
+            lines = fh.read().split("\n")
+        lines[1] = "%d       // Number of time segments  " % ts
+        with open(p, "w", newline="") as fh:
+            fh.write("\n".join(lines))
+    if gains is not None:
+        p = os.path.join(tmp, "problems", mission, "gains.param")
+        os.chmod(p, 0o644)
+        with open(p, "w", newline="") as fh:
+            fh.write("//edited gains\n" + "\n".join("%r   // gain" % float(g) for g in gains))
     return tmp + "/", tmp
 
 
@@ -75,10 +82,10 @@ class RefProblem:
     """One reference `problemG7` / `problemS10` object (reference src/tol.cpp:5-36)."""
 
     def __init__(self, mission, aircraft, enu=(0.0, 0.0, 70.0), goal=(0.0, 0.0, 0.0, 0.0), ts=None,
-                 null_io=True):
+                 gains=None, null_io=True):
         L = lib()
         L.tolref_set_null_io(1 if null_io else 0)
-        root, self._tmp = make_root(ts, mission)
+        root, self._tmp = make_root(ts, mission, gains)
         self.mission, self.aircraft = mission, aircraft
         self.h = L.tolref_create(mission.encode(), aircraft.encode(), *[float(v) for v in enu],
                                  *[float(v) for v in goal], root.encode())

@@ -1,0 +1,97 @@
+"""CPU: the host side of libtolcuda that needs no device -- the C-ABI surface, the closed-form
+sparsity pattern (vs the reference's and vs the oracle's literal countG walk) and the .param reader."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import tol_b200 as T
+from conftest import GOLDEN, GOLDEN_DIR, ROOT, load_golden
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "tolcuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(tolcuda_[a-z_0-9]+|DEFINEGusrfg_)\s*\(", hdr))
+    assert {"tolcuda_create", "tolcuda_eval", "tolcuda_eval_batch", "tolcuda_pattern", "tolcuda_dims",
+            "tolcuda_bind_global", "tolcuda_destroy", "DEFINEGusrfg_"} <= names
+    L = ctypes.CDLL(T.LIB_PATH)
+    for nm in sorted(names):
+        assert hasattr(L, nm), "libtolcuda.so does not export " + nm
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_closed_form_pattern_equals_reference(name):
+    g = load_golden(name)
+    m, ts = str(g["mission"]), int(g["ts"])
+    assert T.problem_dims(m, ts) == (int(g["n"]), int(g["neF"]), int(g["neG"]))
+    i, j = T.problem_pattern(m, ts)
+    assert i.dtype == np.int32 and np.array_equal(i, g["iGfun"]) and np.array_equal(j, g["jGvar"])
+
+
+@pytest.mark.parametrize("mission", ["G7", "S10"])
+def test_closed_form_pattern_equals_countg_walk_for_every_small_ts(oracle_built, mission):
+    g = load_golden("G7_skywalker_ts2" if mission == "G7" else "S10_tempest_ts1")
+    for ts in list(range(1, 41)) + [64, 65, 127, 128, 129]:
+        p = oracle_built.PortProblem(mission, ts, g["ac"], g["gn"], g["goal_ned"], 1)
+        assert T.problem_dims(mission, ts) == (p.n, p.neF, p.neG)
+        i, j = T.problem_pattern(mission, ts)
+        oi, oj = p.pattern()
+        assert np.array_equal(i, oi) and np.array_equal(j, oj), ts
+
+
+def test_read_params_quirks(tmp_path):
+    p = tmp_path / "q.param"
+    # header comment, CRLF, literal backslash-n after the number, '/' as the real delimiter, blank and
+    # text-only lines skipped, exponent and sign forms, last line without newline
+    p.write_bytes(b"//header 12 // not a value\r\n4\\n    \t// Mass (kg)\r\n2.42\\n\t// span\n\n"
+                  b"  -0.45\\n // min CL\nnot a number\n1e20 / single slash\n.5e-1//x\n7/3\n+3.0")
+    v, cnt = T.read_params(p)
+    assert cnt == 7
+    assert v.tolist() == [4.0, 2.42, -0.45, 1e20, 0.05, 7.0, 3.0]
+    with pytest.raises(T.TolcudaError):
+        T.read_params(tmp_path / "missing.param")
+
+
+def test_read_params_matches_reference_files():
+    ref = "/root/reference/"
+    if not os.path.isdir(ref):
+        ref = os.path.join(ROOT, "oracle", "_ref", "params") + "/"
+    if not os.path.isdir(os.path.join(ref, "aircraft")):
+        pytest.skip("reference .param files not present")
+    P = json.load(open(os.path.join(GOLDEN_DIR, "params.json")))
+    for ac, want in P["aircraft"].items():
+        v, cnt = T.read_params(os.path.join(ref, "aircraft", ac + ".param"))
+        assert cnt == 15
+        v[8], v[11], v[12] = v[8] * np.pi / 180.0, v[11] * np.pi / 180.0, v[12] * np.pi / 180.0
+        assert v.tolist() == want, ac
+    for ms, d in P["problems"].items():
+        v, cnt = T.read_params(os.path.join(ref, "problems", ms, "gains.param"))
+        assert cnt == 5 and v.tolist() == d["gains"]
+        v, cnt = T.read_params(os.path.join(ref, "problems", ms, "snopt.param"))
+        assert cnt == 6 and v.tolist() == d["snopt"]
+        v, cnt = T.read_params(os.path.join(ref, "problems", ms, "limits.param"))
+        lm = d["limits_member_order"]  # dtmin,dtmax,xmax,ymax,zmax,xmin,ymin,zmin
+        assert cnt == 8 and v.tolist() == [lm[0], lm[1], lm[5], lm[2], lm[6], lm[3], lm[7], lm[4]]
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    g = load_golden("S10_tempest_ts1")
+    with pytest.raises(T.TolcudaError):
+        T.Evaluator.from_golden(g)
+
+
+def test_synthetic_batch_is_shard_invariant():
+    g = load_golden("G7_skywalker_ts2")
+    x0 = g["x"][0]
+    full = T.synth.batch(x0, 99, 0, 10)
+    parts = [T.synth.batch(x0, 99, *T.synth.shard_range(10, r, 4)) for r in range(4)]
+    assert np.array_equal(full, np.concatenate(parts))
+    # fixture sample s >= 1 is perturb(x0, seed0 + s - 1)
+    assert np.array_equal(g["x"][1], T.synth.perturb(x0, int(g["seed0"])))

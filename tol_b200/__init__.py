@@ -1,0 +1,6 @@
+"""tol_b200 -- Python test/bench harness over libtolcuda (the B200-native evaluator of tol's SNOPT
+user function).  The product is the C-ABI library declared in include/tolcuda.h; this package only
+loads it, moves buffers and launches one process per GPU.  Nothing here computes F or G."""
+from .lib import LIB_PATH, TolcudaError, load  # noqa: F401
+from .evaluator import Evaluator, G7, S10, problem_dims, problem_pattern, read_params  # noqa: F401
+from . import synth  # noqa: F401

@@ -1,0 +1,41 @@
+// Constants one tolcuda context uploads to __constant__ memory once, at create time.
+//
+// They replace the reference's `aircraft ac`, `gain gn`, `snopt sn` members and goal fields that
+// every gradient call re-reads (reference include/problem.h:50-53,81-83, include/parameters.h:22-74).
+// Products of constants are stored pre-multiplied ONLY where the reference's own left-to-right
+// association forms exactly that product (e.g. `rho*ac.SS*Va...` starts with (rho*SS)), so the
+// kernels reproduce the reference's rounding sequence.
+#ifndef TOLCUDA_FG_CONST_H_
+#define TOLCUDA_FG_CONST_H_
+
+#define TOLCUDA_MAX_CTX 64 /* live contexts per process (constant-memory slots) */
+#define TOLCUDA_PX 11      /* numinp,    problems/<M>/snopt.param line 3 */
+#define TOLCUDA_PF 8       /* numstates, problems/<M>/snopt.param line 4 */
+#define TOLCUDA_REC 104    /* G values per collocation window: 8 defect rows x 13 columns */
+
+struct FgConst {
+    int form, ts, wind, nb;
+    int n, neF, neG;
+    int R0;    // length of the objective-row block = G offset of window 0's record
+    int nbG;   // length of the boundary block (33 for S10, 42 for G7)
+    int pad_;
+    double mm;       // ac.mm
+    double SS;       // ac.SS
+    double rho;      // include/problem.h:73
+    double g;        // include/problem.h:72
+    double Cd0;      // ac.Cd0
+    double rhoSS;    // rho*ac.SS
+    double ARpiee;   // ac.AR*M_PI*ac.ee
+    double ARpieemm; // ac.AR*M_PI*ac.ee*ac.mm
+    double twomm;    // 2.0*ac.mm
+    double kT, kp, kdt;
+    double half_kT;  // 0.5*gn.kT (== gn.kT*0.5)
+    double half_kp;  // 0.5*gn.kp
+    double kv_ts;    // gn.kv*sn.ts
+    double kp_ts;    // gn.kp*sn.ts
+    double xg, yg, rg;
+    double cos_chid, sin_chid; // cos/sin of chi_d = atan2(yg - yi, xg - xi), src/problemG7.cpp:524
+    double wind_Wxz;           // dWx_dz = -dv_dz = -(-Vref/href), src/problem.cpp:524,975
+};
+
+#endif

@@ -1,0 +1,458 @@
+// libtolcuda C ABI (include/tolcuda.h): contexts, constant upload, streams, pinned staging and the
+// host/device batch paths around the sm_100a kernels of fg_kernels.cu.  No CPU evaluation path
+// exists in this library: if CUDA is unavailable every evaluation call fails with the CUDA error.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+#include "fg_launch.h"
+#include "tolcuda_internal.h"
+
+#define TOLCUDA_VERSION "0.1.0"
+
+namespace tolcuda {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+
+static int cuda_fail(cudaError_t e, const char *what) {
+    set_error(std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+    return (int)e;
+}
+
+#define CU(call)                                          \
+    do {                                                  \
+        cudaError_t e_ = (call);                          \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+}  // namespace tolcuda
+
+using namespace tolcuda;
+
+// One staging lane of the host-pointer batch path: device buffers for a chunk of trajectories and
+// the stream that carries H2D -> kernel -> D2H for that chunk.
+struct BatchLane {
+    cudaStream_t stream = nullptr;
+    double *d_x = nullptr, *d_F = nullptr, *d_G = nullptr;
+    int cap = 0;  // trajectories
+};
+
+struct tolcuda_ctx {
+    tolcuda_config cfg;
+    FgConst c;
+    int slot = -1;
+    int npp = 8;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::vector<int> iG, jG;
+    // single-trajectory path: pinned host staging + device buffers, allocated once
+    double *h_one = nullptr;  // [n | neF | neG], pinned
+    double *d_one = nullptr;  // same layout on the device
+    long ox = 0, oF = 0, oG = 0;
+    // host-pointer batch path
+    BatchLane lane[2];
+    long launches = 0;
+};
+
+namespace {
+
+std::mutex g_mu;
+bool g_slot_used[TOLCUDA_MAX_CTX];
+tolcuda_ctx *g_bound = nullptr;
+
+int take_slot() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (int i = 0; i < TOLCUDA_MAX_CTX; i++)
+        if (!g_slot_used[i]) {
+            g_slot_used[i] = true;
+            return i;
+        }
+    return -1;
+}
+
+void release_slot(int s) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (s >= 0) g_slot_used[s] = false;
+}
+
+long round_up(long v, long m) { return (v + m - 1) / m * m; }
+
+int launch(tolcuda_ctx *h, cudaStream_t st, int B, const double *x, long ldx, double *F, long ldF,
+           double *G, long ldG, int needF, int needG) {
+    FgLaunch L;
+    L.slot = h->slot;
+    L.form = h->c.form, L.wind = h->c.wind, L.ts = h->c.ts;
+    L.n = h->c.n, L.neF = h->c.neF, L.R0 = h->c.R0;
+    L.B = B;
+    L.x = x, L.ldx = ldx, L.F = F, L.ldF = ldF, L.G = G, L.ldG = ldG;
+    L.needF = needF, L.needG = needG;
+    L.npp = h->npp;
+    L.stream = st;
+    cudaError_t e = fg_launch(L);
+    if (e != cudaSuccess) return cuda_fail(e, "fg_launch");
+    h->launches++;
+    return 0;
+}
+
+void free_lane(BatchLane &l) {
+    if (l.d_x) cudaFree(l.d_x);
+    if (l.d_F) cudaFree(l.d_F);
+    if (l.d_G) cudaFree(l.d_G);
+    if (l.stream) cudaStreamDestroy(l.stream);
+    l = BatchLane();
+}
+
+int ensure_lane(tolcuda_ctx *h, BatchLane &l, int cap) {
+    if (!l.stream) CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    if (l.cap >= cap) return 0;
+    if (l.d_x) cudaFree(l.d_x);
+    if (l.d_F) cudaFree(l.d_F);
+    if (l.d_G) cudaFree(l.d_G);
+    l.d_x = l.d_F = l.d_G = nullptr;
+    l.cap = 0;
+    const long ldx = tolcuda_padded_ld(h->c.n), ldF = tolcuda_padded_ld(h->c.neF),
+               ldG = tolcuda_padded_ld(h->c.neG);
+    CU(cudaMalloc(&l.d_x, sizeof(double) * ldx * cap));
+    CU(cudaMalloc(&l.d_F, sizeof(double) * ldF * cap));
+    CU(cudaMalloc(&l.d_G, sizeof(double) * ldG * cap));
+    l.cap = cap;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *tolcuda_last_error(void) { return g_err.c_str(); }
+const char *tolcuda_version(void) { return TOLCUDA_VERSION; }
+
+long tolcuda_padded_ld(long len) { return round_up(len, 16); }
+
+int tolcuda_read_params(const char *path, double *values, int cap, int *count) {
+    if (!path || !count) return TOLCUDA_EINVAL;
+    std::vector<double> v;
+    int e = read_params(path, v);
+    if (e) {
+        set_error(std::string("cannot open parameter file ") + path);
+        return e;
+    }
+    *count = (int)v.size();
+    for (int i = 0; i < cap && i < (int)v.size(); i++) values[i] = v[i];
+    return 0;
+}
+
+int tolcuda_create(const tolcuda_config *cfg, tolcuda_handle *out) {
+    if (!cfg || !out) return TOLCUDA_EINVAL;
+    *out = nullptr;
+    if (cfg->formulation != TOLCUDA_G7 && cfg->formulation != TOLCUDA_S10) {
+        set_error("formulation must be TOLCUDA_G7 or TOLCUDA_S10");
+        return TOLCUDA_EUNSUPPORTED;
+    }
+    if (cfg->wind_model != TOLCUDA_WIND_NONE && cfg->wind_model != TOLCUDA_WIND_LINEAR_LAYER) {
+        set_error("wind model not built (0 = none, 1 = linear boundary layer)");
+        return TOLCUDA_EUNSUPPORTED;
+    }
+    if (cfg->ts < 1 || cfg->ts > 1024) {
+        set_error("ts must be in 1..1024 (one CTA owns one trajectory)");
+        return TOLCUDA_EUNSUPPORTED;
+    }
+    tolcuda_ctx *h = new (std::nothrow) tolcuda_ctx();
+    if (!h) return TOLCUDA_ENOMEM;
+    h->cfg = *cfg;
+    FgConst &c = h->c;
+    std::memset(&c, 0, sizeof c);
+    c.form = cfg->formulation;
+    c.ts = cfg->ts;
+    c.wind = cfg->wind_model;
+    c.nb = c.form == TOLCUDA_G7 ? 12 : 11;
+    pattern_dims(c.form, c.ts, &c.n, &c.neF, &c.neG, &c.R0, &c.nbG);
+    const double *ac = cfg->aircraft, *gn = cfg->gains;
+    const double mm = ac[0], SS = ac[2], ee = ac[3], AR = ac[4], Cd0 = ac[5];
+    c.mm = mm, c.SS = SS, c.Cd0 = Cd0;
+    c.rho = 1.2682;  // reference include/problem.h:73
+    c.g = 9.81;      // reference include/problem.h:72
+    c.rhoSS = c.rho * SS;
+    c.ARpiee = AR * M_PI * ee;
+    c.ARpieemm = AR * M_PI * ee * mm;
+    c.twomm = 2.0 * mm;
+    c.kT = gn[0], c.kp = gn[1], c.kdt = gn[4];
+    c.half_kT = 0.5 * gn[0];
+    c.half_kp = 0.5 * gn[1];
+    c.kv_ts = gn[2] * c.ts;
+    c.kp_ts = gn[1] * c.ts;
+    c.xg = cfg->goal[0], c.yg = cfg->goal[1], c.rg = cfg->goal[3];
+    // chi_d = atan2(yg - yi, xg - xi) with the hard-coded xi = yi = 0 of the reference constructor
+    // (src/problemG7.cpp:524, src/problem.cpp:111-112); host libm, as in the reference
+    const double chi_d = std::atan2(c.yg - 0.0, c.xg - 0.0);
+    c.cos_chid = std::cos(chi_d);
+    c.sin_chid = std::sin(chi_d);
+    {
+        const double Vref = 2.4, href = 10;  // src/problem.cpp:504-505
+        const double dv_dz = -Vref / href;   // :524
+        c.wind_Wxz = -dv_dz;                 // :975
+    }
+    pattern_build(c.form, c.ts, h->iG, h->jG);
+
+    const char *env = std::getenv("TOLCUDA_NPP");
+    if (env) {
+        int v = std::atoi(env);
+        if (v == 8 || v == 16 || v == 32) h->npp = v;
+    }
+
+    int rc = 0;
+    do {
+        cudaError_t e = cudaSetDevice(cfg->device);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaSetDevice"); break; }
+        h->slot = take_slot();
+        if (h->slot < 0) {
+            set_error("too many live tolcuda contexts");
+            rc = TOLCUDA_ENOMEM;
+            break;
+        }
+        e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaStreamCreate"); break; }
+        h->stream = h->own_stream;
+        e = fg_upload_const(h->slot, c, h->stream);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "constant upload"); break; }
+        h->ox = 0;
+        h->oF = tolcuda_padded_ld(c.n);
+        h->oG = h->oF + tolcuda_padded_ld(c.neF);
+        const size_t bytes = sizeof(double) * (h->oG + tolcuda_padded_ld(c.neG));
+        e = cudaMallocHost(&h->h_one, bytes);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMallocHost"); break; }
+        e = cudaMalloc(&h->d_one, bytes);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc"); break; }
+    } while (0);
+    if (rc) {
+        tolcuda_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return 0;
+}
+
+int tolcuda_create_from_files(const char *root, const char *aircraft, const char *mission,
+                              double east, double north, double up, double east_goal,
+                              double north_goal, double up_goal, double radius_goal,
+                              int ts_override, int device, tolcuda_handle *out) {
+    (void)east, (void)north, (void)up;  // stored by the reference, unused on the evaluation path
+    if (!root || !aircraft || !mission || !out) return TOLCUDA_EINVAL;
+    tolcuda_config cfg;
+    std::memset(&cfg, 0, sizeof cfg);
+    const std::string ms(mission);
+    if (ms == "G7") cfg.formulation = TOLCUDA_G7;
+    else if (ms == "S10") cfg.formulation = TOLCUDA_S10;
+    else {
+        set_error("Problem " + ms + " not recognized.");  // reference src/problem.cpp:361
+        return TOLCUDA_EUNSUPPORTED;
+    }
+    int e;
+    if ((e = read_aircraft(root, aircraft, cfg.aircraft))) return e;
+    if ((e = read_gains(root, ms, cfg.gains))) return e;
+    double sn[6];
+    if ((e = read_snopt(root, ms, sn))) return e;
+    const int nb = cfg.formulation == TOLCUDA_G7 ? 12 : 11;
+    if ((int)sn[1] != TOLCUDA_PX || (int)sn[2] != TOLCUDA_PF || (int)sn[3] != nb) {
+        set_error("snopt.param: numinp/numstates/numbounds differ from the built formulation");
+        return TOLCUDA_EUNSUPPORTED;
+    }
+    cfg.ts = ts_override > 0 ? ts_override : (int)sn[0];
+    cfg.wind_model = TOLCUDA_WIND_LINEAR_LAYER;  // what the reference falls back to, src/problem.cpp:77
+    cfg.device = device;
+    // ENU -> NED, reference src/problem.cpp:24-27
+    cfg.goal[0] = north_goal;
+    cfg.goal[1] = east_goal;
+    cfg.goal[2] = -up_goal;
+    cfg.goal[3] = radius_goal;
+    return tolcuda_create(&cfg, out);
+}
+
+int tolcuda_destroy(tolcuda_handle h) {
+    if (!h) return 0;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (g_bound == h) g_bound = nullptr;
+    }
+    cudaSetDevice(h->cfg.device);
+    if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+    free_lane(h->lane[0]);
+    free_lane(h->lane[1]);
+    if (h->h_one) cudaFreeHost(h->h_one);
+    if (h->d_one) cudaFree(h->d_one);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    release_slot(h->slot);
+    delete h;
+    return 0;
+}
+
+int tolcuda_dims(tolcuda_handle h, int *n, int *neF, int *neG) {
+    if (!h) return TOLCUDA_EINVAL;
+    if (n) *n = h->c.n;
+    if (neF) *neF = h->c.neF;
+    if (neG) *neG = h->c.neG;
+    return 0;
+}
+
+int tolcuda_pattern(tolcuda_handle h, int *iGfun, int *jGvar) {
+    if (!h || !iGfun || !jGvar) return TOLCUDA_EINVAL;
+    std::memcpy(iGfun, h->iG.data(), sizeof(int) * h->iG.size());
+    std::memcpy(jGvar, h->jG.data(), sizeof(int) * h->jG.size());
+    return 0;
+}
+
+int tolcuda_problem_dims(int formulation, int ts, int *n, int *neF, int *neG) {
+    if ((formulation != TOLCUDA_G7 && formulation != TOLCUDA_S10) || ts < 1) return TOLCUDA_EINVAL;
+    pattern_dims(formulation, ts, n, neF, neG, nullptr, nullptr);
+    return 0;
+}
+
+int tolcuda_problem_pattern(int formulation, int ts, int *iGfun, int *jGvar) {
+    if ((formulation != TOLCUDA_G7 && formulation != TOLCUDA_S10) || ts < 1 || !iGfun || !jGvar)
+        return TOLCUDA_EINVAL;
+    std::vector<int> iG, jG;
+    pattern_build(formulation, ts, iG, jG);
+    std::memcpy(iGfun, iG.data(), sizeof(int) * iG.size());
+    std::memcpy(jGvar, jG.data(), sizeof(int) * jG.size());
+    return 0;
+}
+
+int tolcuda_set_stream(tolcuda_handle h, void *cuda_stream) {
+    if (!h) return TOLCUDA_EINVAL;
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return 0;
+}
+
+int tolcuda_synchronize(tolcuda_handle h) {
+    if (!h) return TOLCUDA_EINVAL;
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+long tolcuda_launch_count(tolcuda_handle h) { return h ? h->launches : 0; }
+
+int tolcuda_eval(tolcuda_handle h, const double *x, int needF, double *F, int needG, double *G) {
+    if (!h || !x || (needF > 0 && !F) || (needG > 0 && !G)) return TOLCUDA_EINVAL;
+    if (needF <= 0 && needG <= 0) return 0;
+    const FgConst &c = h->c;
+    CU(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    std::memcpy(h->h_one + h->ox, x, sizeof(double) * c.n);
+    CU(cudaMemcpyAsync(h->d_one + h->ox, h->h_one + h->ox, sizeof(double) * c.n, cudaMemcpyHostToDevice, st));
+    int rc = launch(h, st, 1, h->d_one + h->ox, c.n, h->d_one + h->oF, c.neF, h->d_one + h->oG, c.neG,
+                    needF > 0, needG > 0);
+    if (rc) return rc;
+    if (needF > 0)
+        CU(cudaMemcpyAsync(h->h_one + h->oF, h->d_one + h->oF, sizeof(double) * c.neF, cudaMemcpyDeviceToHost, st));
+    if (needG > 0)
+        CU(cudaMemcpyAsync(h->h_one + h->oG, h->d_one + h->oG, sizeof(double) * c.neG, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (needF > 0) std::memcpy(F, h->h_one + h->oF, sizeof(double) * c.neF);
+    if (needG > 0) std::memcpy(G, h->h_one + h->oG, sizeof(double) * c.neG);
+    return 0;
+}
+
+int tolcuda_eval_batch(tolcuda_handle h, int B, const double *x, long ldx, double *F, long ldF,
+                       double *G, long ldG, int flags) {
+    if (!h || B < 0) return TOLCUDA_EINVAL;
+    const int needF = (flags & TOLCUDA_NEED_F) != 0, needG = (flags & TOLCUDA_NEED_G) != 0;
+    if (B == 0 || (!needF && !needG)) return 0;
+    const FgConst &c = h->c;
+    if (!x || ldx < c.n || (needF && (!F || ldF < c.neF)) || (needG && (!G || ldG < c.neG))) {
+        set_error("tolcuda_eval_batch: null pointer or leading dimension shorter than the row");
+        return TOLCUDA_EINVAL;
+    }
+    CU(cudaSetDevice(h->cfg.device));
+    bool host = (flags & TOLCUDA_HOST_PTRS) != 0;
+    if (!host && !(flags & TOLCUDA_DEVICE_PTRS)) {
+        cudaPointerAttributes at;
+        cudaError_t e = cudaPointerGetAttributes(&at, x);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            host = true;
+        } else {
+            host = !(at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged);
+        }
+    }
+    if (!host) {
+        int rc = launch(h, h->stream, B, x, ldx, F, ldF, G, ldG, needF, needG);
+        if (rc) return rc;
+        if (!(flags & TOLCUDA_NO_SYNC)) CU(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+
+    // Host pointers: chunks of trajectories alternate between two lanes; each lane's stream carries
+    // H2D(x) -> kernel -> D2H(F, G) for its chunk, so one lane's copies overlap the other's kernel.
+    const long dldx = tolcuda_padded_ld(c.n), dldF = tolcuda_padded_ld(c.neF), dldG = tolcuda_padded_ld(c.neG);
+    const size_t per_traj = sizeof(double) * (size_t)(dldx + dldF + dldG);
+    size_t budget = (size_t)256 << 20;  // device bytes per lane
+    if (const char *env = std::getenv("TOLCUDA_CHUNK_MB")) {
+        long mb = std::atol(env);
+        if (mb > 0) budget = (size_t)mb << 20;
+    }
+    int chunk = (int)std::max<size_t>(1, budget / per_traj);
+    chunk = std::min(chunk, B);
+    if (B > chunk && B < 2 * chunk) chunk = (B + 1) / 2;
+    for (int l = 0; l < 2; l++) {
+        if (l == 1 && B <= chunk) break;
+        int rc = ensure_lane(h, h->lane[l], chunk);
+        if (rc) return rc;
+    }
+    int li = 0;
+    for (int b0 = 0; b0 < B; b0 += chunk, li ^= 1) {
+        BatchLane &l = h->lane[li];
+        const int nb = std::min(chunk, B - b0);
+        CU(cudaMemcpy2DAsync(l.d_x, sizeof(double) * dldx, x + (size_t)b0 * ldx, sizeof(double) * ldx,
+                             sizeof(double) * c.n, nb, cudaMemcpyHostToDevice, l.stream));
+        int rc = launch(h, l.stream, nb, l.d_x, dldx, l.d_F, dldF, l.d_G, dldG, needF, needG);
+        if (rc) return rc;
+        if (needF)
+            CU(cudaMemcpy2DAsync(F + (size_t)b0 * ldF, sizeof(double) * ldF, l.d_F, sizeof(double) * dldF,
+                                 sizeof(double) * c.neF, nb, cudaMemcpyDeviceToHost, l.stream));
+        if (needG)
+            CU(cudaMemcpy2DAsync(G + (size_t)b0 * ldG, sizeof(double) * ldG, l.d_G, sizeof(double) * dldG,
+                                 sizeof(double) * c.neG, nb, cudaMemcpyDeviceToHost, l.stream));
+    }
+    CU(cudaStreamSynchronize(h->lane[0].stream));
+    if (h->lane[1].stream) CU(cudaStreamSynchronize(h->lane[1].stream));
+    return 0;
+}
+
+int tolcuda_bind_global(tolcuda_handle h) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_bound = h;
+    return 0;
+}
+
+void DEFINEGusrfg_(int *Status, int *n, double x[], int *needF, int *neF, double F[], int *needG,
+                   int *neG, double G[], char *cu, int *lencu, int iu[], int *leniu, double ru[],
+                   int *lenru) {
+    (void)cu, (void)lencu, (void)iu, (void)leniu, (void)ru, (void)lenru;  // unused, as in the reference
+    tolcuda_ctx *h;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        h = g_bound;
+    }
+    int rc;
+    if (!h) {
+        set_error("DEFINEGusrfg_: no context bound (call tolcuda_bind_global first)");
+        rc = TOLCUDA_ENOCTX;
+    } else if ((n && *n != h->c.n) || (neF && *needF > 0 && *neF != h->c.neF) ||
+               (neG && *needG > 0 && *neG != h->c.neG)) {
+        set_error("DEFINEGusrfg_: n/neF/neG differ from the bound context's problem");
+        rc = TOLCUDA_EINVAL;
+    } else {
+        rc = tolcuda_eval(h, x, *needF, F, *needG, G);
+    }
+    if (rc) {
+        std::fprintf(stderr, "tolcuda: user function failed (%d): %s\n", rc, tolcuda_last_error());
+        if (Status) *Status = -2;  // SNOPT: terminate
+    }
+}
+
+}  // extern "C"

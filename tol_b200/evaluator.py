@@ -1,0 +1,149 @@
+"""Thin object wrapper over the libtolcuda C ABI: one Evaluator == one `tolcuda_handle`, i.e. what a
+reference `problemG7` / `problemS10` object is to the reference callback (src/tol.cpp:5-36).  Every
+evaluation goes through the C entry points a C/C++ caller would use."""
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _l
+
+G7, S10 = 7, 10
+NEED_F, NEED_G = 0x1, 0x2
+HOST_PTRS, DEVICE_PTRS, NO_SYNC = 0x10, 0x20, 0x40
+_FORM = {"G7": G7, "S10": S10, G7: G7, S10: S10}
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def problem_dims(mission, ts):
+    n, neF, neG = C.c_int(), C.c_int(), C.c_int()
+    _l.check(_l.load().tolcuda_problem_dims(_FORM[mission], int(ts), C.byref(n), C.byref(neF),
+                                            C.byref(neG)))
+    return n.value, neF.value, neG.value
+
+
+def problem_pattern(mission, ts):
+    _, _, neG = problem_dims(mission, ts)
+    i, j = np.empty(neG, np.int32), np.empty(neG, np.int32)
+    _l.check(_l.load().tolcuda_problem_pattern(_FORM[mission], int(ts), _ip(i), _ip(j)))
+    return i, j
+
+
+def read_params(path, cap=64):
+    v = np.zeros(cap)
+    cnt = C.c_int()
+    _l.check(_l.load().tolcuda_read_params(str(path).encode(), _dp(v), cap, C.byref(cnt)))
+    return v[:min(cnt.value, cap)].copy(), cnt.value
+
+
+def padded_ld(n):
+    return int(_l.load().tolcuda_padded_ld(int(n)))
+
+
+class Evaluator:
+    def __init__(self, mission, ts, aircraft, gains, goal_ned, wind_model=1, device=0):
+        L = _l.load()
+        cfg = _l.Config()
+        cfg.formulation, cfg.ts, cfg.wind_model, cfg.device = _FORM[mission], int(ts), int(wind_model), int(device)
+        cfg.aircraft[:] = [float(v) for v in aircraft]
+        cfg.gains[:] = [float(v) for v in gains]
+        cfg.goal[:] = [float(v) for v in goal_ned]
+        self.h = C.c_void_p()
+        _l.check(L.tolcuda_create(C.byref(cfg), C.byref(self.h)))
+        self._finish(L, device)
+
+    @classmethod
+    def from_files(cls, root, aircraft, mission, enu=(0.0, 0.0, 0.0), goal_enu=(0.0, 0.0, 0.0, 0.0),
+                   ts=0, device=0):
+        L = _l.load()
+        self = cls.__new__(cls)
+        self.h = C.c_void_p()
+        _l.check(L.tolcuda_create_from_files(str(root).encode(), aircraft.encode(), mission.encode(),
+                                             *[float(v) for v in enu], *[float(v) for v in goal_enu],
+                                             int(ts), int(device), C.byref(self.h)))
+        self._finish(L, device)
+        return self
+
+    @classmethod
+    def from_golden(cls, g, device=0, wind_model=None):
+        """g: an opened tests/golden/*.npz fixture"""
+        wm = int(g["wind_model"]) if wind_model is None else wind_model
+        return cls(str(g["mission"]), int(g["ts"]), g["ac"], g["gn"], g["goal_ned"], wm, device)
+
+    def _finish(self, L, device):
+        self.L, self.device = L, device
+        n, neF, neG = C.c_int(), C.c_int(), C.c_int()
+        _l.check(L.tolcuda_dims(self.h, C.byref(n), C.byref(neF), C.byref(neG)))
+        self.n, self.neF, self.neG = n.value, neF.value, neG.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.tolcuda_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def pattern(self):
+        i, j = np.empty(self.neG, np.int32), np.empty(self.neG, np.int32)
+        _l.check(self.L.tolcuda_pattern(self.h, _ip(i), _ip(j)))
+        return i, j
+
+    def eval(self, x, needF=True, needG=True):
+        """tolcuda_eval: one trajectory, host arrays"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.size == self.n
+        F = np.full(self.neF, np.nan)
+        G = np.full(self.neG, np.nan)
+        _l.check(self.L.tolcuda_eval(self.h, _dp(x), int(needF), _dp(F), int(needG), _dp(G)))
+        return F, G
+
+    def usrfun(self, x, needF=1, needG=1, bind=True):
+        """call the exported snOptA callback DEFINEGusrfg_ exactly as SNOPT would"""
+        if bind:
+            _l.check(self.L.tolcuda_bind_global(self.h))
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        F = np.full(self.neF, np.nan)
+        G = np.full(self.neG, np.nan)
+        st = C.c_int(0)
+        ints = [C.c_int(v) for v in (self.n, needF, self.neF, needG, self.neG, 0, 0, 0)]
+        n_, nf_, neF_, ng_, neG_, lencu, leniu, lenru = ints
+        self.L.DEFINEGusrfg_(C.byref(st), C.byref(n_), _dp(x), C.byref(nf_), C.byref(neF_), _dp(F),
+                             C.byref(ng_), C.byref(neG_), _dp(G), None, C.byref(lencu), None,
+                             C.byref(leniu), None, C.byref(lenru))
+        return st.value, F, G
+
+    def eval_batch_host(self, X, F=None, G=None, needF=True, needG=True):
+        """tolcuda_eval_batch with HOST arrays (numpy, or pinned torch tensors via .numpy())"""
+        B = X.shape[0]
+        assert X.dtype == np.float64 and X.strides[1] == 8
+        if F is None:
+            F = np.empty((B, self.neF))
+        if G is None:
+            G = np.empty((B, self.neG))
+        flags = (NEED_F if needF else 0) | (NEED_G if needG else 0) | HOST_PTRS
+        _l.check(self.L.tolcuda_eval_batch(self.h, B, X.ctypes.data, X.strides[0] // 8, F.ctypes.data,
+                                           F.strides[0] // 8, G.ctypes.data, G.strides[0] // 8, flags))
+        return F, G
+
+    def eval_batch_device(self, X, F, G, needF=True, needG=True, sync=True):
+        """tolcuda_eval_batch with torch CUDA tensors [B, ld] (float64, row-contiguous)"""
+        B = X.shape[0]
+        flags = (NEED_F if needF else 0) | (NEED_G if needG else 0) | DEVICE_PTRS | (0 if sync else NO_SYNC)
+        _l.check(self.L.tolcuda_eval_batch(self.h, B, X.data_ptr(), X.stride(0), F.data_ptr(), F.stride(0),
+                                           G.data_ptr(), G.stride(0), flags))
+
+    def set_stream(self, cuda_stream_ptr):
+        _l.check(self.L.tolcuda_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        _l.check(self.L.tolcuda_synchronize(self.h))
+
+    @property
+    def launches(self):
+        return int(self.L.tolcuda_launch_count(self.h))

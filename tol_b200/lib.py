@@ -1,0 +1,63 @@
+"""ctypes binding of libtolcuda.so (include/tolcuda.h).  The library is built in-tree by
+`make -C tol_b200/csrc` (see __graft_entry__.build); a missing library is an error, never a
+fallback."""
+import ctypes as C
+import os
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtolcuda.so")
+
+
+class TolcudaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("tolcuda error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Config(C.Structure):
+    """struct tolcuda_config"""
+    _fields_ = [("formulation", C.c_int), ("ts", C.c_int), ("wind_model", C.c_int),
+                ("device", C.c_int), ("aircraft", C.c_double * 15), ("gains", C.c_double * 5),
+                ("goal", C.c_double * 4)]
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libtolcuda.so is not built (%s): run `python -c 'import __graft_entry__ as g; "
+                          "g.build()'` or `make -C tol_b200/csrc`; there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p
+    L.tolcuda_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.tolcuda_create_from_files.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p] + [C.c_double] * 7 + \
+        [C.c_int, C.c_int, C.POINTER(vp)]
+    L.tolcuda_destroy.argtypes = [vp]
+    L.tolcuda_dims.argtypes = [vp, ip, ip, ip]
+    L.tolcuda_pattern.argtypes = [vp, ip, ip]
+    L.tolcuda_problem_dims.argtypes = [C.c_int, C.c_int, ip, ip, ip]
+    L.tolcuda_problem_pattern.argtypes = [C.c_int, C.c_int, ip, ip]
+    L.tolcuda_eval.argtypes = [vp, dp, C.c_int, dp, C.c_int, dp]
+    L.tolcuda_eval_batch.argtypes = [vp, C.c_int, vp, C.c_long, vp, C.c_long, vp, C.c_long, C.c_int]
+    L.tolcuda_padded_ld.argtypes = [C.c_long]
+    L.tolcuda_padded_ld.restype = C.c_long
+    L.tolcuda_set_stream.argtypes = [vp, vp]
+    L.tolcuda_synchronize.argtypes = [vp]
+    L.tolcuda_launch_count.argtypes = [vp]
+    L.tolcuda_launch_count.restype = C.c_long
+    L.tolcuda_bind_global.argtypes = [vp]
+    L.DEFINEGusrfg_.argtypes = [ip, ip, dp, ip, ip, dp, ip, ip, dp, C.c_char_p, ip, ip, ip, dp, ip]
+    L.DEFINEGusrfg_.restype = None
+    L.tolcuda_read_params.argtypes = [C.c_char_p, dp, C.c_int, ip]
+    L.tolcuda_last_error.restype = C.c_char_p
+    L.tolcuda_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise TolcudaError(rc, load().tolcuda_last_error().decode(errors="replace"))
