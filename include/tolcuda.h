@@ -101,9 +101,11 @@ int tolcuda_eval_batch(tolcuda_handle h, int B, const double *x, long ldx, doubl
 /* smallest multiple of 16 doubles (128 bytes) that holds `len` doubles */
 long tolcuda_padded_ld(long len);
 
-/* run the context's work on a caller-owned cudaStream_t (e.g. torch's current stream) so that the
- * caller's CUDA events bracket the kernels; NULL restores the context's own stream */
+/* run the context's single-trajectory and device-pointer work on a caller-owned cudaStream_t (e.g.
+ * torch's current stream) so that the caller's CUDA events bracket the kernels.  NULL is the legacy
+ * default stream, as everywhere in CUDA; tolcuda_use_own_stream goes back to the context's own. */
 int tolcuda_set_stream(tolcuda_handle h, void *cuda_stream);
+int tolcuda_use_own_stream(tolcuda_handle h);
 int tolcuda_synchronize(tolcuda_handle h);
 
 /* number of kernel launches this context has issued (bench.py's gpu_launches) */

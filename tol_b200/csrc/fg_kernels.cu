@@ -23,11 +23,12 @@
 // for finite y, so this changes no value (only, possibly, the sign of a zero).  What is left to
 // differ from the reference is the last-ulp behaviour of sin/cos (CUDA libdevice vs glibc).
 //
-// Memory.  The trajectory's decision vector (n doubles, contiguous) is staged in shared memory with
-// coalesced 16-byte loads; every output leaves through shared memory as full coalesced 16-byte
-// stores: the 104-value Jacobian record of each window is assembled in a per-warp tile whose
-// structural constants (0, +-1, -dt) are written once per CTA, and F plus the objective row are
-// staged in the (by then dead) x buffer.  Cost sums use warp-shuffle reductions.
+// Memory.  Each warp stages the 33-node slice of x its 32 windows need in shared memory with
+// coalesced 16-byte loads, and every output leaves through the warp's shared tile as coalesced
+// 16-byte stores: the 104-value Jacobian record of a window goes out as four 26-value quarter
+// records (two defect rows each; a 26-double lane stride is bank-conflict-free for 16-byte
+// accesses), then the objective-row entries, then the 8 defects.  Cost sums use warp-shuffle
+// reductions; warps of a trajectory meet only through an arrival counter in shared memory.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -42,40 +43,115 @@ namespace {
 constexpr int PX = TOLCUDA_PX;
 constexpr int PF = TOLCUDA_PF;
 constexpr int REC = TOLCUDA_REC;
-constexpr int REC_LD = 106;  // smem stride of a record: 16-byte aligned, and with 8 bytes x (2*106)
-                             // words the 8/16 lanes of a pass hit distinct banks
-constexpr int NVAR = 31;     // x-dependent entries of a record
+constexpr int QREC = 26;                 // a quarter record: two defect rows x 13 columns
+constexpr int SX_LEN = 1 + PX * 33 + 2;  // a warp's x slice: dt slot + 33 nodes, rounded to even
+constexpr int TILE_LEN = 32 * QREC;      // doubles; also holds the F (32 x 10) and objective-row passes
+constexpr int WARP_SMEM = SX_LEN + TILE_LEN;
+constexpr int F_LD = 10;                 // smem stride of a window's 8 defects (== 2 mod 4: no conflicts)
 
-// ---- per-window arithmetic ----------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
 
-struct WindowOut {
-    double f[PF];    // defects F[1+8k .. 8+8k]
-    double v[NVAR];  // x-dependent Jacobian entries, order = kVarIdx
-};
+__device__ __forceinline__ void st2(double *p, double a, double b) {
+    *reinterpret_cast<double2 *>(p) = make_double2(a, b);
+}
 
-// record positions of WindowOut::v (row s starts at 13*s: [d/d dt, d/d c0..c10 @k, d/d c_s @k+1])
-__device__ constexpr int kVarIdx[NVAR] = {
-    0,  4,  5,  6,           // F1: dt, Va, gam, chi        src/problem.cpp:1084-1088
-    13, 17, 18, 19,          // F2                          :1098-1102
-    26, 30, 31,              // F3: dt, Va, gam             :1112-1115
-    39, 43, 44, 45, 47, 50,  // F4: dt, Va, gam, chi, CL, T :1125-1130
-    52, 56, 57, 58, 59, 60,  // F5: dt, Va, gam, chi, phi, CL :1140-1145
-    65, 69, 70, 71, 72, 73,  // F6                          :1155-1160
-    78,                      // F7: dt                      :1172
-    91};                     // F8: dt                      :1184
+// Copy `chunks` pieces of 2*HALF doubles each from a dense shared tile to global memory where piece c
+// starts at dst + c*dst_stride: consecutive lanes take consecutive 16-byte words of the tile, so
+// every warp store covers 512 contiguous tile bytes (a run of whole pieces in global memory).
+template <int HALF>
+__device__ __forceinline__ void tile_out_vec(double *__restrict__ dst, int dst_stride,
+                                             const double *__restrict__ tile, int chunks, int lane) {
+    const int total = chunks * HALF;
+#pragma unroll
+    for (int it = 0; it < HALF; it++) {
+        const int i = lane + 32 * it;
+        if (i < total) {
+            const int c = i / HALF, j = i - c * HALF;
+            *reinterpret_cast<double2 *>(dst + (size_t)c * dst_stride + 2 * j) =
+                *reinterpret_cast<const double2 *>(tile + 2 * i);
+        }
+    }
+}
 
-template <int WIND>
-__device__ __forceinline__ void window_eval(const FgConst &c, const double *__restrict__ s0,
-                                            const double *__restrict__ s1, double dt, bool needG,
-                                            WindowOut &o) {
+template <int LEN>
+__device__ __forceinline__ void tile_out_scalar(double *__restrict__ dst, int dst_stride,
+                                                const double *__restrict__ tile, int chunks, int lane) {
+    const int total = chunks * LEN;
+#pragma unroll
+    for (int it = 0; it < LEN; it++) {
+        const int i = lane + 32 * it;
+        if (i < total) {
+            const int c = i / LEN, j = i - c * LEN;
+            dst[(size_t)c * dst_stride + j] = tile[i];
+        }
+    }
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------
+//
+// grid.x = B trajectories, blockDim.x = 32*ceil(ts/32) (<= MAXT).  Warp w owns windows 32w..32w+31
+// and runs on its own: it stages its 33-node slice of x, evaluates, and streams its outputs through
+// its private shared tile in passes (4 quarter-records of the Jacobian, the objective-row entries,
+// the defects), each pass ending in coalesced 16-byte global stores.  No block barrier after start-up:
+// the cost sum crosses warps through shared memory and an arrival counter, and the last warp to
+// arrive writes F[0], the boundary rows and the objective-row ends.
+template <int FORM, int WIND, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+fg_batch_kernel(int slot, const double *__restrict__ x, long ldx, double *__restrict__ F, long ldF,
+                double *__restrict__ G, long ldG, int needF, int needG) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double red[2][32];
+    __shared__ int arrivals;
     constexpr bool W = (WIND == 1);
+    constexpr bool S10 = (FORM == TOLCUDA_FORM_S10);
+    const FgConst &c = c_fg[slot];
+    const int ts = c.ts;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    double *sx = smem + (size_t)warp * WARP_SMEM;
+    double *tile = sx + SX_LEN;
+
+    const size_t b = blockIdx.x;
+    const double *xb = x + b * ldx;
+    double *Fb = F + b * ldF;
+    double *Gb = G + b * ldG;
+
+    if (threadIdx.x == 0) arrivals = 0;
+    __syncthreads();
+
+    // ---- stage this warp's x slice: doubles [11*k0, 11*k0 + 1 + 11*(nk+1)) of the trajectory ----
+    const int k0 = 32 * warp;
+    const int nk = min(32, ts - k0);          // windows of this warp (>= 1)
+    const int cnt = 1 + PX * (nk + 1);        // slot 0 is x[11*k0] (dt for warp 0, unused otherwise)
+    const double *xs = xb + (size_t)PX * k0;  // even offset: 16-byte aligned whenever xb is
+    if ((reinterpret_cast<uintptr_t>(xs) & 15) == 0) {
+#pragma unroll
+        for (int it = 0; it < (SX_LEN / 2 + 31) / 32; it++) {
+            const int i = lane + 32 * it;
+            if (2 * i + 1 < cnt) st2(sx + 2 * i, __ldg(xs + 2 * i), __ldg(xs + 2 * i + 1));
+            else if (2 * i < cnt) sx[2 * i] = __ldg(xs + 2 * i);
+        }
+    } else {
+        for (int i = lane; i < cnt; i += 32) sx[i] = __ldg(xs + i);
+    }
+    const double dt = __ldg(xb);
+    __syncwarp();
+
+    const int k = k0 + lane;
+    const bool active = lane < nk;
+    const double *s0 = sx + 1 + PX * (active ? lane : 0);
+    const double *s1 = s0 + PX;
     const double z = s0[2], Va = s0[3], gam = s0[4], chi = s0[5], phi = s0[6], CL = s0[7];
     const double dphi = s0[8], dCL = s0[9], T = s0[10];
+
+    // ---- shared sub-expressions of the window (see window formulas in the file header) ----
     double sc, cc, sg, cg, sp, cp;
     sincos(chi, &sc, &cc);
     sincos(gam, &sg, &cg);
     sincos(phi, &sp, &cp);
-
     // wind, NED <- ENU (src/problem.cpp:522-524, 970-981): Wx = v = -Vref*zs/href with zs = -z,
     // dWx_dz = -dv_dz; every other component is exactly zero under models 0 and 1
     const double Wxz = c.wind_Wxz;
@@ -84,7 +160,6 @@ __device__ __forceinline__ void window_eval(const FgConst &c, const double *__re
         const double zs = -z;
         Wx = -2.4 * zs / 10.0;
     }
-
     // (Wx + Va*cos(chi)*cos(gam)), (Wy + Va*cos(gam)*sin(chi)), (Wz - Va*sin(gam))
     const double Vacc = Va * cc, Vacg = Va * cg, Vasg = Va * sg;
     const double vx = W ? Wx + Vacc * cg : Vacc * cg;
@@ -101,7 +176,6 @@ __device__ __forceinline__ void window_eval(const FgConst &c, const double *__re
         ez = -((Wxz * cg) * sc);  // (dWy_dz*cc*cg - dWx_dz*cg*sc)
         fz = -(Wxzsc * sg);       // (dWy_dz*cc*sg - dWx_dz*sc*sg)
     }
-
     const double CdT = c.Cd0 + (CL * CL) / c.ARpiee;  // (Cd0 + CL*CL/(AR*pi*ee))
     const double rSV = c.rhoSS * Va;                  // rho*SS*Va
     const double CLrS = CL * c.rho * c.SS;            // CL*rho*SS
@@ -109,380 +183,310 @@ __device__ __forceinline__ void window_eval(const FgConst &c, const double *__re
     const double Va2 = Va * Va;
     const double Tmm = T / c.mm;
     const double gsg = c.g * sg, gcg = c.g * cg;
-
-    // ---- rhs, src/problem.cpp:1003-1008 ----
-    const double drag3 = (rSV * Va * CdT) / c.twomm;
-    const double dx3 = W ? Tmm - vz * az - gsg - drag3 : Tmm - gsg - drag3;
     const double n4 = W ? vz * bz - gcg : -gcg;  // (vx*bx + vy*by + vz*bz - g*cos(gam))
-    const double dx4 = (n4 + (CLrSV * Va * cp) / c.twomm) / Va;
-    const double lift5 = (CLrSV * Va * sp) / c.twomm;
-    const double dx5 = W ? -(vz * cz - lift5) / Vacg : -(-lift5) / Vacg;
-
-    // ---- defects, src/problem.cpp:1012-1019 ----
-    o.f[0] = s1[0] - vx * dt - s0[0];
-    o.f[1] = s1[1] - vy * dt - s0[1];
-    o.f[2] = s1[2] - vz * dt - s0[2];
-    o.f[3] = s1[3] - dx3 * dt - s0[3];
-    o.f[4] = s1[4] - dx4 * dt - s0[4];
-    o.f[5] = s1[5] - dx5 * dt - s0[5];
-    o.f[6] = s1[6] - dphi * dt - s0[6];
-    o.f[7] = s1[7] - dCL * dt - s0[7];
-    if (!needG) return;
-
-    // ---- Jacobian rows, src/problem.cpp:1074-1192 ----
     const double Vadt = Va * dt, mdt = -dt;
-    double *v = o.v;
-    // F1 :1084-1088
-    v[0] = -vx;
-    v[1] = mdt * cc * cg;
-    v[2] = Vadt * cc * sg;
-    v[3] = Vadt * cg * sc;
-    // F2 :1098-1102
-    v[4] = -vy;
-    v[5] = mdt * cg * sc;
-    v[6] = Vadt * sc * sg;
-    v[7] = -(Vadt * cc * cg);
-    // F3 :1112-1115
-    v[8] = Vasg;
-    v[9] = dt * sg;
-    v[10] = Vadt * cg;
-    // F4 :1125-1130
-    {
-        const double dragv = (rSV * CdT) / c.mm;
-        const double drag11 = (c.rhoSS * Va2 * CdT) / c.twomm;
-        v[11] = W ? vz * az - Tmm + gsg + drag11 : -Tmm + gsg + drag11;
-        v[12] = W ? dt * (-(sg * az) + dragv) - 1.0 : dt * dragv - 1.0;
-        v[13] = W ? mdt * (n4 + Vacg * az) : mdt * n4;
-        v[14] = W ? dt * (ez * vz) : 0.0;
-        v[15] = (CLrS * Va2 * dt) / c.ARpieemm;
-        v[16] = mdt / c.mm;
-    }
-    // F5 :1140-1145
-    {
-        const double S5 = n4 + (CLrS * Va2 * cp) / c.twomm;
-        const double liftv = (CLrSV * cp) / c.mm;
-        v[17] = -S5 / Va;
-        v[18] = W ? (dt * S5) / Va2 - (dt * (-(sg * bz) + liftv)) / Va
-                  : (dt * S5) / Va2 - (dt * liftv) / Va;
-        v[19] = W ? -(dt * (vz * az + gsg - Vacg * bz)) / Va - 1.0 : -(dt * gsg) / Va - 1.0;
-        v[20] = W ? -(dt * (fz * vz)) / Va : 0.0;
-        v[21] = (CLrSV * dt * sp) / c.twomm;
-        v[22] = -(rSV * dt * cp) / c.twomm;
-    }
-    // F6 :1155-1160
-    {
-        const double lift6 = (CLrS * Va2 * sp) / c.twomm;
-        const double Q = W ? vz * cz - lift6 : -lift6;
-        const double sidev = (CLrSV * sp) / c.mm;
-        v[23] = Q / Vacg;
-        v[24] = W ? -(dt * (sg * cz + sidev)) / Vacg - (dt * Q) / (Va2 * cg)
-                  : -(dt * sidev) / Vacg - (dt * Q) / (Va2 * cg);
-        v[25] = W ? (dt * sg * Q) / (Va * (cg * cg)) - (dt * (Vacg * cz)) / Vacg
-                  : (dt * sg * Q) / (Va * (cg * cg));
-        v[26] = W ? -(dt * (vz * dz)) / Vacg - 1.0 : -1.0;
-        v[27] = -(CLrSV * dt * cp) / (c.twomm * cg);
-        v[28] = -(rSV * dt * sp) / (c.twomm * cg);
-    }
-    v[29] = -dphi;  // F7 :1172
-    v[30] = -dCL;   // F8 :1184
-}
 
-// structural constants of a record (tabG zero-initialisation and the +-1 / -dt entries,
-// src/problem.cpp:1038, 1084, 1098, 1112, 1170-1171, 1182-1183, 1204), x-dependent entries zeroed
-__device__ __forceinline__ void record_init(double *rec, double dt) {
-    double2 *r2 = reinterpret_cast<double2 *>(rec);
-#pragma unroll
-    for (int j = 0; j < REC / 2; j++) r2[j] = make_double2(0.0, 0.0);
-    rec[1] = -1.0;   // F1 d/dx
-    rec[15] = -1.0;  // F2 d/dy
-    rec[29] = -1.0;  // F3 d/dz
-    rec[85] = -1.0;  // F7 d/dphi
-    rec[87] = -dt;   // F7 d/ddphi
-    rec[99] = -1.0;  // F8 d/dCL
-    rec[101] = -dt;  // F8 d/ddCL
-#pragma unroll
-    for (int s = 0; s < PF; s++) rec[13 * s + 12] = 1.0;  // d/d(state s at node k+1)
-}
-
-__device__ __forceinline__ void record_store(double *rec, const double *v) {
-#pragma unroll
-    for (int i = 0; i < NVAR; i++) {
-        // adjacent (even, odd) positions go out as one 16-byte store
-        if (i + 1 < NVAR && (kVarIdx[i] % 2 == 0) && kVarIdx[i + 1] == kVarIdx[i] + 1) {
-            *reinterpret_cast<double2 *>(rec + kVarIdx[i]) = make_double2(v[i], v[i + 1]);
-            i++;
-        } else {
-            rec[kVarIdx[i]] = v[i];
+    double *q = tile + QREC * lane;  // this lane's quarter record (stride 26 doubles: conflict-free)
+    if (needG) {
+        double *Grec = Gb + c.R0 + (size_t)REC * k0;
+        const bool vec = (reinterpret_cast<uintptr_t>(Grec) & 15) == 0;
+        // ---- rows F1, F2: src/problem.cpp:1084-1088, 1098-1102 ----
+        if (active) {
+            st2(q + 0, -vx, -1.0);
+            st2(q + 2, 0.0, 0.0);
+            st2(q + 4, mdt * cc * cg, Vadt * cc * sg);
+            st2(q + 6, Vadt * cg * sc, 0.0);
+            st2(q + 8, 0.0, 0.0);
+            st2(q + 10, 0.0, 0.0);
+            st2(q + 12, 1.0, -vy);
+            st2(q + 14, 0.0, -1.0);
+            st2(q + 16, 0.0, mdt * cg * sc);
+            st2(q + 18, Vadt * sc * sg, -(Vadt * cc * cg));
+            st2(q + 20, 0.0, 0.0);
+            st2(q + 22, 0.0, 0.0);
+            st2(q + 24, 0.0, 1.0);
         }
-    }
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-    return v;
-}
-
-// coalesced copy of `count` doubles from shared to global by `nthr` threads; 16-byte stores when both
-// sides allow it
-__device__ __forceinline__ void copy_out(double *__restrict__ dst, const double *__restrict__ src,
-                                         int count, int tid, int nthr) {
-    const bool vec = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0;
-    if (vec) {
-        const int pairs = count >> 1;
-        for (int i = tid; i < pairs; i += nthr)
-            reinterpret_cast<double2 *>(dst)[i] = reinterpret_cast<const double2 *>(src)[i];
-        if ((count & 1) && tid == 0) dst[count - 1] = src[count - 1];
-    } else {
-        for (int i = tid; i < count; i += nthr) dst[i] = src[i];
-    }
-}
-
-// ---- the kernel -----------------------------------------------------------------------------------
-//
-// grid.x = B trajectories, blockDim.x = 32*ceil(ts/32) (<= MAXT <= 1024).  Dynamic shared memory:
-//   sbuf [max(n, neF + R0) rounded to even]   x slice, later the F / objective-row staging area
-//   tile [warps][NPP][REC_LD]                 Jacobian records of NPP consecutive windows per warp
-//   red  [2][32]                              cross-warp cost sums
-template <int FORM, int WIND, int NPP, int MAXT>
-__global__ void __launch_bounds__(MAXT)
-fg_batch_kernel(int slot, const double *__restrict__ x, long ldx, double *__restrict__ F, long ldF,
-                double *__restrict__ G, long ldG, int needF, int needG, int sbuf_len) {
-    extern __shared__ __align__(16) double smem[];
-    const FgConst &c = c_fg[slot];
-    const int ts = c.ts, n = c.n;
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    const int nwarps = nthr >> 5;
-    double *sbuf = smem;
-    double *tile = smem + sbuf_len + (size_t)warp * (NPP * REC_LD);
-    double *red = smem + sbuf_len + (size_t)nwarps * (NPP * REC_LD);
-
-    const size_t b = blockIdx.x;
-    const double *xb = x + b * ldx;
-    double *Fb = F + b * ldF;
-    double *Gb = G + b * ldG;
-
-    // ---- stage x: coalesced, 16 bytes per lane when the trajectory is 16-byte aligned ----
-    if ((reinterpret_cast<uintptr_t>(xb) & 15) == 0) {
-        const double2 *x2 = reinterpret_cast<const double2 *>(xb);
-        double2 *s2 = reinterpret_cast<double2 *>(sbuf);
-        for (int i = tid; i < (n >> 1); i += nthr) s2[i] = __ldg(x2 + i);
-        if ((n & 1) && tid == 0) sbuf[n - 1] = __ldg(xb + n - 1);
-    } else {
-        for (int i = tid; i < n; i += nthr) sbuf[i] = __ldg(xb + i);
-    }
-    const double dt_pre = __ldg(xb);  // every lane needs dt before the barrier for record_init
-    if (needG && lane < NPP) record_init(tile + lane * REC_LD, dt_pre);
-    __syncthreads();
-
-    const double dt = sbuf[0];
-    const int k = tid;
-    const bool active = k < ts;
-    WindowOut o;
-    double sumT = 0.0, sump = 0.0;     // cost partial sums
-    double r0x = 0.0, r0y = 0.0, r0T = 0.0;  // this node's objective-row entries
-    double rex = 0.0, rey = 0.0, reT = 0.0;  // node ts's, held by the thread of window ts-1
-    if (active) {
-        const double *s0 = sbuf + 1 + PX * k;
-        window_eval<WIND>(c, s0, s0 + PX, dt, needG != 0, o);
-        // ---- objective terms: src/problemS10.cpp:246-258, 340-372; src/problemG7.cpp:240-241, 370
-        const double T = s0[10];
-        sumT = T * T;
-        r0T = c.kT * T;
-        if (FORM == TOLCUDA_FORM_S10) {
-            const double ddx = s0[0] - c.xg, ddy = s0[1] - c.yg;
-            const double r = sqrt(ddx * ddx + ddy * ddy);
-            const double rmR = r - c.rg;
-            sump = rmR * rmR;
-            r0x = c.kp * rmR * ddx / r;
-            r0y = c.kp * rmR * ddy / r;
+        __syncwarp();
+        if (vec) tile_out_vec<QREC / 2>(Grec, REC, tile, nk, lane);
+        else tile_out_scalar<QREC>(Grec, REC, tile, nk, lane);
+        __syncwarp();
+        // ---- rows F3, F4: :1112-1115, :1125-1130 ----
+        if (active) {
+            const double dragv = (rSV * CdT) / c.mm;
+            const double drag11 = (c.rhoSS * Va2 * CdT) / c.twomm;
+            const double g4dt = W ? vz * az - Tmm + gsg + drag11 : -Tmm + gsg + drag11;
+            const double g4Va = W ? dt * (-(sg * az) + dragv) - 1.0 : dt * dragv - 1.0;
+            const double g4gam = W ? mdt * (n4 + Vacg * az) : mdt * n4;
+            const double g4chi = W ? dt * (ez * vz) : 0.0;
+            const double g4CL = (CLrS * Va2 * dt) / c.ARpieemm;
+            const double g4T = mdt / c.mm;
+            st2(q + 0, Vasg, 0.0);
+            st2(q + 2, 0.0, -1.0);
+            st2(q + 4, dt * sg, Vadt * cg);
+            st2(q + 6, 0.0, 0.0);
+            st2(q + 8, 0.0, 0.0);
+            st2(q + 10, 0.0, 0.0);
+            st2(q + 12, 1.0, g4dt);
+            st2(q + 14, 0.0, 0.0);
+            st2(q + 16, 0.0, g4Va);
+            st2(q + 18, g4gam, g4chi);
+            st2(q + 20, 0.0, g4CL);
+            st2(q + 22, 0.0, 0.0);
+            st2(q + 24, g4T, 1.0);
         }
-        if (k == ts - 1) {
-            const double *se = s0 + PX;
-            const double Te = se[10];
-            sumT += Te * Te;
-            reT = c.kT * Te;
-            if (FORM == TOLCUDA_FORM_S10) {
-                const double ddx = se[0] - c.xg, ddy = se[1] - c.yg;
+        __syncwarp();
+        if (vec) tile_out_vec<QREC / 2>(Grec + QREC, REC, tile, nk, lane);
+        else tile_out_scalar<QREC>(Grec + QREC, REC, tile, nk, lane);
+        __syncwarp();
+        // ---- rows F5, F6: :1140-1145, :1155-1160 ----
+        if (active) {
+            const double S5 = n4 + (CLrS * Va2 * cp) / c.twomm;
+            const double liftv = (CLrSV * cp) / c.mm;
+            const double g5dt = -S5 / Va;
+            const double g5Va = W ? (dt * S5) / Va2 - (dt * (-(sg * bz) + liftv)) / Va
+                                  : (dt * S5) / Va2 - (dt * liftv) / Va;
+            const double g5gam = W ? -(dt * (vz * az + gsg - Vacg * bz)) / Va - 1.0 : -(dt * gsg) / Va - 1.0;
+            const double g5chi = W ? -(dt * (fz * vz)) / Va : 0.0;
+            const double g5phi = (CLrSV * dt * sp) / c.twomm;
+            const double g5CL = -(rSV * dt * cp) / c.twomm;
+            const double lift6 = (CLrS * Va2 * sp) / c.twomm;
+            const double Q = W ? vz * cz - lift6 : -lift6;
+            const double sidev = (CLrSV * sp) / c.mm;
+            const double g6dt = Q / Vacg;
+            const double g6Va = W ? -(dt * (sg * cz + sidev)) / Vacg - (dt * Q) / (Va2 * cg)
+                                  : -(dt * sidev) / Vacg - (dt * Q) / (Va2 * cg);
+            const double g6gam = W ? (dt * sg * Q) / (Va * (cg * cg)) - (dt * (Vacg * cz)) / Vacg
+                                   : (dt * sg * Q) / (Va * (cg * cg));
+            const double g6chi = W ? -(dt * (vz * dz)) / Vacg - 1.0 : -1.0;
+            const double g6phi = -(CLrSV * dt * cp) / (c.twomm * cg);
+            const double g6CL = -(rSV * dt * sp) / (c.twomm * cg);
+            st2(q + 0, g5dt, 0.0);
+            st2(q + 2, 0.0, 0.0);
+            st2(q + 4, g5Va, g5gam);
+            st2(q + 6, g5chi, g5phi);
+            st2(q + 8, g5CL, 0.0);
+            st2(q + 10, 0.0, 0.0);
+            st2(q + 12, 1.0, g6dt);
+            st2(q + 14, 0.0, 0.0);
+            st2(q + 16, 0.0, g6Va);
+            st2(q + 18, g6gam, g6chi);
+            st2(q + 20, g6phi, g6CL);
+            st2(q + 22, 0.0, 0.0);
+            st2(q + 24, 0.0, 1.0);
+        }
+        __syncwarp();
+        if (vec) tile_out_vec<QREC / 2>(Grec + 2 * QREC, REC, tile, nk, lane);
+        else tile_out_scalar<QREC>(Grec + 2 * QREC, REC, tile, nk, lane);
+        __syncwarp();
+        // ---- rows F7, F8: :1170-1172, :1182-1184 ----
+        if (active) {
+            st2(q + 0, -dphi, 0.0);
+            st2(q + 2, 0.0, 0.0);
+            st2(q + 4, 0.0, 0.0);
+            st2(q + 6, 0.0, -1.0);
+            st2(q + 8, 0.0, mdt);
+            st2(q + 10, 0.0, 0.0);
+            st2(q + 12, 1.0, -dCL);
+            st2(q + 14, 0.0, 0.0);
+            st2(q + 16, 0.0, 0.0);
+            st2(q + 18, 0.0, 0.0);
+            st2(q + 20, 0.0, -1.0);
+            st2(q + 22, 0.0, mdt);
+            st2(q + 24, 0.0, 1.0);
+        }
+        __syncwarp();
+        if (vec) tile_out_vec<QREC / 2>(Grec + 3 * QREC, REC, tile, nk, lane);
+        else tile_out_scalar<QREC>(Grec + 3 * QREC, REC, tile, nk, lane);
+        __syncwarp();
+    }
+
+    // ---- objective terms: src/problemS10.cpp:246-258, 340-372; src/problemG7.cpp:240-241, 370 ----
+    double sumT = 0.0, sump = 0.0;
+    {
+        const bool last_window = active && (k == ts - 1);  // also carries node ts
+        double r0x = 0.0, r0y = 0.0, rex = 0.0, rey = 0.0;
+        const double Te = s1[10];
+        if (active) sumT = T * T;
+        if (last_window) sumT += Te * Te;
+        if (S10) {
+            if (active) {
+                const double ddx = s0[0] - c.xg, ddy = s0[1] - c.yg;
+                const double r = sqrt(ddx * ddx + ddy * ddy);
+                const double rmR = r - c.rg;
+                sump = rmR * rmR;
+                r0x = c.kp * rmR * ddx / r;
+                r0y = c.kp * rmR * ddy / r;
+            }
+            if (last_window) {
+                const double ddx = s1[0] - c.xg, ddy = s1[1] - c.yg;
                 const double r = sqrt(ddx * ddx + ddy * ddy);
                 const double rmR = r - c.rg;
                 sump += rmR * rmR;
                 rex = c.kp * rmR * ddx / r;
                 rey = c.kp * rmR * ddy / r;
             }
-        }
-    }
-
-    // ---- Jacobian records: NPP windows per pass through the warp's tile, then one coalesced copy ----
-    if (needG) {
-        const int kwarp = warp * 32;
-        double *Grec = Gb + c.R0 + (size_t)REC * kwarp;
-        const bool vec = (reinterpret_cast<uintptr_t>(Grec) & 15) == 0;
-#pragma unroll 1
-        for (int pass = 0; pass < 32 / NPP; pass++) {
-            const int kbase = kwarp + pass * NPP;
-            if (kbase >= ts) break;
-            const int valid = min(NPP, ts - kbase);
-            if (active && (lane / NPP) == pass) record_store(tile + (lane % NPP) * REC_LD, o.v);
-            __syncwarp();
-            double *dst = Grec + (size_t)REC * (pass * NPP);
-            if (vec) {
-                for (int i = lane; i < valid * (REC / 2); i += 32) {
-                    const int node = i / (REC / 2), j = i - node * (REC / 2);
-                    reinterpret_cast<double2 *>(dst)[i] =
-                        *reinterpret_cast<const double2 *>(tile + node * REC_LD + 2 * j);
-                }
-            } else {
-                for (int i = lane; i < valid * REC; i += 32) {
-                    const int node = i / REC, j = i - node * REC;
-                    dst[i] = tile[node * REC_LD + j];
-                }
-            }
-            __syncwarp();
-        }
-    }
-
-    // ---- cost sums: warp shuffle, then across warps ----
-    sumT = warp_sum(sumT);
-    if (FORM == TOLCUDA_FORM_S10) sump = warp_sum(sump);
-    if (lane == 0) {
-        red[warp] = sumT;
-        red[32 + warp] = sump;
-    }
-    // endpoints used by the G7 objective / boundary rows (read before sbuf is recycled)
-    const double x0 = sbuf[1], y0 = sbuf[2];
-    const double xf = sbuf[1 + PX * ts], yf = sbuf[2 + PX * ts];
-    double bnd[PX];  // thread 0: node ts minus node 0, per state
-    if (tid == 0) {
-#pragma unroll
-        for (int cidx = 0; cidx < PX; cidx++) bnd[cidx] = sbuf[1 + PX * ts + cidx] - sbuf[1 + cidx];
-    }
-    __syncthreads();  // every thread is done reading x: sbuf becomes the output staging area
-
-    double *sF = sbuf;            // [neF]
-    double *sRow0 = sbuf + c.neF; // [R0] (S10 only; G7's objective row is written directly)
-    if (active && needF) {
-#pragma unroll
-        for (int s = 0; s < PF; s++) sF[1 + PF * k + s] = o.f[s];
-    }
-    if (FORM == TOLCUDA_FORM_S10) {
-        if (active && needG) {
-            sRow0[1 + 3 * k] = r0x;
-            sRow0[2 + 3 * k] = r0y;
-            sRow0[3 + 3 * k] = r0T;
-            if (k == ts - 1) {
-                sRow0[1 + 3 * ts] = rex;
-                sRow0[2 + 3 * ts] = rey;
-                sRow0[3 + 3 * ts] = reT;
-            }
-        }
-    } else if (active && needG) {
-        // G7 objective row [dt, x_0, y_0, T_0 .. T_{ts-1}, x_ts, y_ts, T_ts], src/problemG7.cpp:343-380
-        Gb[3 + k] = r0T;
-        if (k == ts - 1) Gb[ts + 5] = reT;
-    }
-    if (tid == 0) {
-        double tT = 0.0, tp = 0.0;
-        for (int w = 0; w < nwarps; w++) {
-            tT += red[w];
-            tp += red[32 + w];
-        }
-        double *Gbnd = Gb + c.R0 + (size_t)REC * ts;
-        if (FORM == TOLCUDA_FORM_S10) {
-            if (needF) {
-                sF[0] = c.half_kT * tT + c.half_kp * tp + c.kdt * dt;  // src/problemS10.cpp:264
-                double *Fbnd = sF + (c.neF - c.nb);                    // src/problemS10.cpp:292-303
-#pragma unroll
-                for (int cidx = 0; cidx < PX; cidx++) Fbnd[cidx] = bnd[cidx];
-                Fbnd[5] = bnd[5] - 2.0 * M_PI;
-            }
             if (needG) {
-                sRow0[0] = c.kdt;  // src/problemS10.cpp:378-381
-                // boundary rows [dt, (0,c), (ts,c)]: the dt entry is uninitialised in the reference
-                // (src/problemS10.cpp:397,414) and DEFINED as 0.0 here
-#pragma unroll
-                for (int cidx = 0; cidx < PX; cidx++) {
-                    Gbnd[3 * cidx] = 0.0;
-                    Gbnd[3 * cidx + 1] = -1.0;
-                    Gbnd[3 * cidx + 2] = 1.0;
+                // objective row [dt, (x, y, T) of every node]: this warp's 3*nk (+3) entries
+                if (active) {
+                    tile[3 * lane] = r0x;
+                    tile[3 * lane + 1] = r0y;
+                    tile[3 * lane + 2] = c.kT * T;
                 }
+                if (last_window) {
+                    tile[3 * lane + 3] = rex;
+                    tile[3 * lane + 4] = rey;
+                    tile[3 * lane + 5] = c.kT * Te;
+                }
+                __syncwarp();
+                const int cnt0 = 3 * nk + ((k0 + nk == ts) ? 3 : 0);
+                double *dst = Gb + 1 + 3 * k0;
+                for (int i = lane; i < cnt0; i += 32) dst[i] = tile[i];
+                __syncwarp();
             }
-        } else {
-            const double ddx = xf - x0, ddy = yf - y0;
-            const double dist = sqrt(ddx * ddx + ddy * ddy);
-            if (needF) {
-                sF[0] = c.half_kT * tT + c.kv_ts * dt / dist;  // src/problemG7.cpp:249
-                double *Fbnd = sF + (c.neF - c.nb);            // src/problemG7.cpp:276-294
-                const double gx = c.xg - x0, gy = c.yg - y0;
+        } else if (needG) {
+            // G7 objective row [dt, x_0, y_0, T_0 .. T_{ts-1}, x_ts, y_ts, T_ts], src/problemG7.cpp:343-380
+            if (active) Gb[3 + k] = c.kT * T;
+            if (last_window) Gb[ts + 5] = c.kT * Te;
+        }
+    }
+
+    // ---- defects, src/problem.cpp:1003-1019 ----
+    if (needF) {
+        if (active) {
+            const double drag3 = (rSV * Va * CdT) / c.twomm;
+            const double dx3 = W ? Tmm - vz * az - gsg - drag3 : Tmm - gsg - drag3;
+            const double dx4 = (n4 + (CLrSV * Va * cp) / c.twomm) / Va;
+            const double lift5 = (CLrSV * Va * sp) / c.twomm;
+            const double dx5 = W ? -(vz * cz - lift5) / Vacg : -(-lift5) / Vacg;
+            double *f = tile + F_LD * lane;
+            st2(f + 0, s1[0] - vx * dt - s0[0], s1[1] - vy * dt - s0[1]);
+            st2(f + 2, s1[2] - vz * dt - s0[2], s1[3] - dx3 * dt - s0[3]);
+            st2(f + 4, s1[4] - dx4 * dt - s0[4], s1[5] - dx5 * dt - s0[5]);
+            st2(f + 6, s1[6] - dphi * dt - s0[6], s1[7] - dCL * dt - s0[7]);
+        }
+        __syncwarp();
+        double *dst = Fb + 1 + PF * k0;
+#pragma unroll
+        for (int it = 0; it < PF; it++) {
+            const int i = lane + 32 * it;  // i-th defect of the warp: window i/8, state i%8
+            if (i < PF * nk) dst[i] = tile[F_LD * (i >> 3) + (i & 7)];
+        }
+    }
+
+    // ---- cost sums: warp shuffle, then across warps through shared memory ----
+    sumT = warp_sum(sumT);
+    if (S10) sump = warp_sum(sump);
+    int last = 0;
+    if (lane == 0) {
+        red[0][warp] = sumT;
+        red[1][warp] = sump;
+        __threadfence_block();
+        last = (atomicAdd(&arrivals, 1) == nwarps - 1);
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence_block();
+
+    // ---- the last warp to arrive: F[0], boundary rows, objective-row ends ----
+    const volatile double *vred = &red[0][0];
+    double tT = 0.0, tp = 0.0;
+    for (int w = 0; w < nwarps; w++) {  // fixed order: deterministic
+        tT += vred[w];
+        tp += vred[32 + w];
+    }
+    const double *xe = xb + (size_t)PX * ts;  // node ts at xe[1..11], node 0 at xb[1..11]
+    double *Fbnd = Fb + (c.neF - c.nb);
+    double *Gbnd = Gb + c.R0 + (size_t)REC * ts;
+    if (S10) {
+        if (needF) {
+            if (lane == 0) Fb[0] = c.half_kT * tT + c.half_kp * tp + c.kdt * dt;  // src/problemS10.cpp:264
+            if (lane < PX) {  // src/problemS10.cpp:292-303
+                double d = __ldg(xe + 1 + lane) - __ldg(xb + 1 + lane);
+                if (lane == 5) d = d - 2.0 * M_PI;
+                Fbnd[lane] = d;
+            }
+        }
+        if (needG) {
+            if (lane == 0) Gb[0] = c.kdt;  // src/problemS10.cpp:378-381
+            // boundary rows [dt, (0,c), (ts,c)]: the dt entry is uninitialised in the reference
+            // (src/problemS10.cpp:397,414) and DEFINED as 0.0 here
+            for (int i = lane; i < 3 * PX; i += 32) {
+                const int m = i % 3;
+                Gbnd[i] = m == 0 ? 0.0 : (m == 1 ? -1.0 : 1.0);
+            }
+        }
+    } else {
+        const double x0 = __ldg(xb + 1), y0 = __ldg(xb + 2), xf = __ldg(xe + 1), yf = __ldg(xe + 2);
+        const double ddx = xf - x0, ddy = yf - y0;
+        const double dist = sqrt(ddx * ddx + ddy * ddy);
+        if (needF) {
+            if (lane == 0) {
+                Fb[0] = c.half_kT * tT + c.kv_ts * dt / dist;  // src/problemG7.cpp:249
+                const double gx = c.xg - x0, gy = c.yg - y0;   // src/problemG7.cpp:276-294
                 const double dmax = sqrt(gx * gx + gy * gy);
                 Fbnd[0] = ddx - dist * c.cos_chid;
                 Fbnd[1] = ddy - dist * c.sin_chid;
-#pragma unroll
-                for (int cidx = 2; cidx < PX; cidx++) Fbnd[cidx] = bnd[cidx];
                 Fbnd[11] = dist - dmax;
             }
-            if (needG) {
-                // objective row ends, src/problemG7.cpp:343-380 (sic: kp, where cost() uses kv)
-                const double d3 = dist * dist * dist;
-                const double gx0 = c.kp_ts * dt * ddx / d3, gy0 = c.kp_ts * dt * ddy / d3;
-                Gb[0] = c.kp_ts / dist;
-                Gb[1] = gx0;
-                Gb[2] = gy0;
-                Gb[ts + 3] = -gx0;
-                Gb[ts + 4] = -gy0;
-                // boundary rows, src/problemG7.cpp:404-511
-                const double ex = ddx / dist, ey = ddy / dist;
-                double *p = Gbnd;
-                p[0] = 0.0, p[1] = -1.0 + ex * c.cos_chid, p[2] = ey * c.cos_chid;
-                p[3] = 1.0 - ex * c.cos_chid, p[4] = -(ey * c.cos_chid);
-                p += 5;
-                p[0] = 0.0, p[1] = ex * c.sin_chid, p[2] = -1.0 + ey * c.sin_chid;
-                p[3] = -(ex * c.sin_chid), p[4] = 1.0 - ey * c.sin_chid;
-                p += 5;
+            if (lane >= 2 && lane < PX) Fbnd[lane] = __ldg(xe + 1 + lane) - __ldg(xb + 1 + lane);
+        }
+        if (needG && lane == 0) {
+            // objective row ends, src/problemG7.cpp:343-380 (sic: kp, where cost() uses kv)
+            const double d3 = dist * dist * dist;
+            const double gx0 = c.kp_ts * dt * ddx / d3, gy0 = c.kp_ts * dt * ddy / d3;
+            Gb[0] = c.kp_ts / dist;
+            Gb[1] = gx0;
+            Gb[2] = gy0;
+            Gb[ts + 3] = -gx0;
+            Gb[ts + 4] = -gy0;
+            // boundary rows, src/problemG7.cpp:404-511
+            const double ex = ddx / dist, ey = ddy / dist;
+            double *p = Gbnd;
+            p[0] = 0.0, p[1] = -1.0 + ex * c.cos_chid, p[2] = ey * c.cos_chid;
+            p[3] = 1.0 - ex * c.cos_chid, p[4] = -(ey * c.cos_chid);
+            p += 5;
+            p[0] = 0.0, p[1] = ex * c.sin_chid, p[2] = -1.0 + ey * c.sin_chid;
+            p[3] = -(ex * c.sin_chid), p[4] = 1.0 - ey * c.sin_chid;
+            p += 5;
 #pragma unroll
-                for (int cidx = 2; cidx < PX; cidx++) {
-                    p[0] = 0.0, p[1] = -1.0, p[2] = 1.0;
-                    p += 3;
-                }
-                p[0] = 0.0, p[1] = -ex, p[2] = -ey, p[3] = ex, p[4] = ey;
+            for (int cidx = 2; cidx < PX; cidx++) {
+                p[0] = 0.0, p[1] = -1.0, p[2] = 1.0;
+                p += 3;
             }
+            p[0] = 0.0, p[1] = -ex, p[2] = -ey, p[3] = ex, p[4] = ey;
         }
     }
-    __syncthreads();
-    if (needF) copy_out(Fb, sF, c.neF, tid, nthr);
-    if (FORM == TOLCUDA_FORM_S10 && needG) copy_out(Gb, sRow0, c.R0, tid, nthr);
 }
 
-template <int FORM, int WIND, int NPP, int MAXT>
+template <int FORM, int WIND, int MAXT, int MINB>
 cudaError_t launch_one(const FgLaunch &L) {
-    auto kern = fg_batch_kernel<FORM, WIND, NPP, MAXT>;
+    auto kern = fg_batch_kernel<FORM, WIND, MAXT, MINB>;
     const int nthr = 32 * ((L.ts + 31) / 32);
-    const int nwarps = nthr / 32;
-    int sbuf_len = L.n > L.neF + L.R0 ? L.n : L.neF + L.R0;
-    sbuf_len = (sbuf_len + 1) & ~1;
-    const size_t smem = sizeof(double) * ((size_t)sbuf_len + (size_t)nwarps * NPP * REC_LD + 64);
+    const size_t smem = sizeof(double) * (size_t)(nthr / 32) * WARP_SMEM;
     static size_t configured = 0;  // per instantiation
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    kern<<<L.B, nthr, smem, L.stream>>>(L.slot, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG,
-                                        sbuf_len);
+    kern<<<L.B, nthr, smem, L.stream>>>(L.slot, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG);
     return cudaGetLastError();
 }
 
 template <int FORM, int WIND>
 cudaError_t launch_npp(const FgLaunch &L) {
-    // 256-thread bound: up to 255 registers per thread; the 1024-thread variant (ts > 256) is
-    // register-capped at 64 and exists for completeness, not speed
-    const bool small = L.ts <= 256;
-    switch (L.npp) {
-    case 8: return small ? launch_one<FORM, WIND, 8, 256>(L) : launch_one<FORM, WIND, 8, 1024>(L);
-    case 16: return small ? launch_one<FORM, WIND, 16, 256>(L) : launch_one<FORM, WIND, 16, 1024>(L);
-    case 32: return small ? launch_one<FORM, WIND, 32, 256>(L) : launch_one<FORM, WIND, 32, 1024>(L);
-    default: return cudaErrorInvalidValue;
+    // register budget per block-size class: 65536 / (MAXT * MINB); L.minb picks a tuning variant
+    if (L.ts <= 128) {
+        if (L.minb == 4) return launch_one<FORM, WIND, 128, 4>(L);
+        if (L.minb == 6) return launch_one<FORM, WIND, 128, 6>(L);
+        return launch_one<FORM, WIND, 128, 5>(L);
     }
+    if (L.ts <= 256) {
+        if (L.minb == 3) return launch_one<FORM, WIND, 256, 3>(L);
+        return launch_one<FORM, WIND, 256, 2>(L);
+    }
+    if (L.ts <= 512) return launch_one<FORM, WIND, 512, 1>(L);
+    return launch_one<FORM, WIND, 1024, 1>(L);
 }
 
 }  // namespace

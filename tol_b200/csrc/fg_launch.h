@@ -20,7 +20,7 @@ struct FgLaunch {
     double *G;
     long ldG;
     int needF, needG;
-    int npp;  // windows per staging pass of a warp: 8, 16 or 32
+    int minb; // tuning variant: minimum resident CTAs per SM the kernel is compiled for (0 = default)
     cudaStream_t stream;
 };
 

@@ -47,7 +47,7 @@ struct tolcuda_ctx {
     tolcuda_config cfg;
     FgConst c;
     int slot = -1;
-    int npp = 8;
+    int minb = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::vector<int> iG, jG;
     // single-trajectory path: pinned host staging + device buffers, allocated once
@@ -91,7 +91,7 @@ int launch(tolcuda_ctx *h, cudaStream_t st, int B, const double *x, long ldx, do
     L.B = B;
     L.x = x, L.ldx = ldx, L.F = F, L.ldF = ldF, L.G = G, L.ldG = ldG;
     L.needF = needF, L.needG = needG;
-    L.npp = h->npp;
+    L.minb = h->minb;
     L.stream = st;
     cudaError_t e = fg_launch(L);
     if (e != cudaSuccess) return cuda_fail(e, "fg_launch");
@@ -198,11 +198,7 @@ int tolcuda_create(const tolcuda_config *cfg, tolcuda_handle *out) {
     }
     pattern_build(c.form, c.ts, h->iG, h->jG);
 
-    const char *env = std::getenv("TOLCUDA_NPP");
-    if (env) {
-        int v = std::atoi(env);
-        if (v == 8 || v == 16 || v == 32) h->npp = v;
-    }
+    if (const char *env = std::getenv("TOLCUDA_MINB")) h->minb = std::atoi(env);
 
     int rc = 0;
     do {
@@ -323,7 +319,13 @@ int tolcuda_problem_pattern(int formulation, int ts, int *iGfun, int *jGvar) {
 
 int tolcuda_set_stream(tolcuda_handle h, void *cuda_stream) {
     if (!h) return TOLCUDA_EINVAL;
-    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    h->stream = (cudaStream_t)cuda_stream;
+    return 0;
+}
+
+int tolcuda_use_own_stream(tolcuda_handle h) {
+    if (!h) return TOLCUDA_EINVAL;
+    h->stream = h->own_stream;
     return 0;
 }
 

@@ -139,7 +139,11 @@ class Evaluator:
                                            G.data_ptr(), G.stride(0), flags))
 
     def set_stream(self, cuda_stream_ptr):
+        """cudaStream_t as an integer (torch: stream.cuda_stream; 0 = legacy default stream)"""
         _l.check(self.L.tolcuda_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def use_own_stream(self):
+        _l.check(self.L.tolcuda_use_own_stream(self.h))
 
     def synchronize(self):
         _l.check(self.L.tolcuda_synchronize(self.h))

@@ -45,6 +45,7 @@ def load():
     L.tolcuda_padded_ld.argtypes = [C.c_long]
     L.tolcuda_padded_ld.restype = C.c_long
     L.tolcuda_set_stream.argtypes = [vp, vp]
+    L.tolcuda_use_own_stream.argtypes = [vp]
     L.tolcuda_synchronize.argtypes = [vp]
     L.tolcuda_launch_count.argtypes = [vp]
     L.tolcuda_launch_count.restype = C.c_long

@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Kernel-only timing helper (device-resident, CUDA events on the launching stream): used to compare
+kernel variants and as the short command that is run under ncu.  Not the bench contract -- bench.py is.
+
+    python tools/kbench.py --workload S10_tempest_ts200 --batch 16384 --steps 10 [--npp 8]"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="S10_tempest_ts200")
+ap.add_argument("--batch", type=int, default=16384)
+ap.add_argument("--steps", type=int, default=10)
+ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--minb", type=int, default=0)
+ap.add_argument("--need", default="FG")
+ap.add_argument("--distinct", type=int, default=512, help="distinct synthetic trajectories (tiled)")
+args = ap.parse_args()
+if args.minb:
+    os.environ["TOLCUDA_MINB"] = str(args.minb)
+import tol_b200 as T  # noqa: E402
+from tol_b200.evaluator import padded_ld  # noqa: E402
+
+g = np.load(os.path.join(ROOT, "tests", "golden", args.workload + ".npz"))
+ev = T.Evaluator.from_golden(g)
+B, n, neF, neG, ts = args.batch, ev.n, ev.neF, ev.neG, int(g["ts"])
+ldx, ldF, ldG = padded_ld(n), padded_ld(neF), padded_ld(neG)
+seed0 = T.synth.SEED_S10 if str(g["mission"]) == "S10" else T.synth.SEED_G7
+U = min(B, args.distinct)
+Xu = torch.zeros(U, ldx, dtype=torch.float64)
+T.synth.batch(g["x"][0], seed0, 0, U, out=Xu.numpy())
+Xd = Xu.cuda()[torch.arange(B, device="cuda") % U].contiguous()
+Fd = torch.empty(B, ldF, dtype=torch.float64, device="cuda")
+Gd = torch.empty(B, ldG, dtype=torch.float64, device="cuda")
+st = torch.cuda.Stream()
+ev.set_stream(st.cuda_stream)
+needF, needG = "F" in args.need, "G" in args.need
+with torch.cuda.stream(st):
+    for _ in range(args.warmup):
+        ev.eval_batch_device(Xd, Fd, Gd, needF, needG, sync=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(args.steps):
+        ev.eval_batch_device(Xd, Fd, Gd, needF, needG, sync=False)
+    e1.record(st)
+    torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / args.steps
+by = 8.0 * B * (n + (neF if needF else 0) + (neG if needG else 0))
+print(json.dumps({"workload": args.workload, "B": B, "minb": args.minb, "need": args.need, "ms": ms,
+                  "node_evals_per_s": B * ts / (ms * 1e-3), "GBps": by / ms / 1e6,
+                  "frac_of_6544": by / ms / 1e6 / 6544.0}))
