@@ -107,10 +107,11 @@ def test_batch_host_pointers_chunked(name, monkeypatch):
 
 @pytest.mark.parametrize("name,seed0", [("G7_skywalker_ts100", T.synth.SEED_G7),
                                         ("S10_tempest_ts200", T.synth.SEED_S10)])
-@pytest.mark.parametrize("minb", [0, 3, 4, 6])
-def test_section_8d_batches_against_oracle(name, seed0, minb, monkeypatch, oracle_built):
-    """configs 3 and 4 of BASELINE.json on a 64-trajectory subset, every compiled occupancy variant"""
-    monkeypatch.setenv("TOLCUDA_MINB", str(minb))
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_section_8d_batches_against_oracle(name, seed0, kernel, monkeypatch, oracle_built):
+    """configs 3 and 4 of BASELINE.json on a 64-trajectory subset, through both kernels (CTA per
+    trajectory / persistent warps)"""
+    monkeypatch.setenv("TOLCUDA_KERNEL", str(kernel))
     g = load_golden(name)
     p = port_from_golden(g)
     B = 64

@@ -1,4 +1,6 @@
-// Constants one tolcuda context uploads to __constant__ memory once, at create time.
+// Constants of one tolcuda context, built once at create time.  Every launch hands them to the kernel
+// as a `const __grid_constant__` parameter, i.e. they live in the constant bank and are used as
+// immediate constant operands (no registers, no loads).
 //
 // They replace the reference's `aircraft ac`, `gain gn`, `snopt sn` members and goal fields that
 // every gradient call re-reads (reference include/problem.h:50-53,81-83, include/parameters.h:22-74).
@@ -8,7 +10,6 @@
 #ifndef TOLCUDA_FG_CONST_H_
 #define TOLCUDA_FG_CONST_H_
 
-#define TOLCUDA_MAX_CTX 64 /* live contexts per process (constant-memory slots) */
 #define TOLCUDA_PX 11      /* numinp,    problems/<M>/snopt.param line 3 */
 #define TOLCUDA_PF 8       /* numstates, problems/<M>/snopt.param line 4 */
 #define TOLCUDA_REC 104    /* G values per collocation window: 8 defect rows x 13 columns */

@@ -36,7 +36,6 @@
 #include "fg_const.h"
 #include "fg_launch.h"
 
-__constant__ FgConst c_fg[TOLCUDA_MAX_CTX];
 
 namespace {
 
@@ -46,7 +45,10 @@ constexpr int REC = TOLCUDA_REC;
 constexpr int QREC = 26;                 // a quarter record: two defect rows x 13 columns
 constexpr int SX_LEN = 1 + PX * 33 + 2;  // a warp's x slice: dt slot + 33 nodes, rounded to even
 constexpr int TILE_LEN = 32 * QREC;      // doubles; also holds the F (32 x 10) and objective-row passes
-constexpr int WARP_SMEM = SX_LEN + TILE_LEN;
+constexpr int WARP_SMEM_A = SX_LEN + TILE_LEN;      // kernel A: one x slice + tile per warp
+constexpr int WARP_SMEM_B = 2 * SX_LEN + TILE_LEN;  // kernel B: double-buffered x slice + tile
+constexpr int WARPS_B = 4;                          // kernel B: warps per CTA
+constexpr int MINB_B = 4;                           // kernel B: CTAs per SM the register budget allows
 constexpr int F_LD = 10;                 // smem stride of a window's 8 defects (== 2 mod 4: no conflicts)
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -91,55 +93,20 @@ __device__ __forceinline__ void tile_out_scalar(double *__restrict__ dst, int ds
     }
 }
 
-// ---- the kernel -----------------------------------------------------------------------------------
+// ---- one warp, one tile of 32 windows ---------------------------------------------------------------
 //
-// grid.x = B trajectories, blockDim.x = 32*ceil(ts/32) (<= MAXT).  Warp w owns windows 32w..32w+31
-// and runs on its own: it stages its 33-node slice of x, evaluates, and streams its outputs through
-// its private shared tile in passes (4 quarter-records of the Jacobian, the objective-row entries,
-// the defects), each pass ending in coalesced 16-byte global stores.  No block barrier after start-up:
-// the cost sum crosses warps through shared memory and an arrival counter, and the last warp to
-// arrive writes F[0], the boundary rows and the objective-row ends.
-template <int FORM, int WIND, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB)
-fg_batch_kernel(int slot, const double *__restrict__ x, long ldx, double *__restrict__ F, long ldF,
-                double *__restrict__ G, long ldG, int needF, int needG) {
-    extern __shared__ __align__(16) double smem[];
-    __shared__ double red[2][32];
-    __shared__ int arrivals;
+// sx: the warp's staged x slice (slot 0 = x[11*k0], node j of the slice at sx[1+11j]); tile: the warp's
+// output staging area.  Writes the tile's share of G (four quarter-record passes + objective-row
+// entries) and of F (defects) and returns the tile's cost partial sums.
+template <int FORM, int WIND>
+__device__ __forceinline__ void tile_eval(const FgConst &c, const double *__restrict__ sx,
+                                          double *__restrict__ tile, const double dt, const int k0,
+                                          const int nk, const int lane, double *__restrict__ Fb,
+                                          double *__restrict__ Gb, const int needF, const int needG,
+                                          double &sumT, double &sump) {
     constexpr bool W = (WIND == 1);
     constexpr bool S10 = (FORM == TOLCUDA_FORM_S10);
-    const FgConst &c = c_fg[slot];
     const int ts = c.ts;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    double *sx = smem + (size_t)warp * WARP_SMEM;
-    double *tile = sx + SX_LEN;
-
-    const size_t b = blockIdx.x;
-    const double *xb = x + b * ldx;
-    double *Fb = F + b * ldF;
-    double *Gb = G + b * ldG;
-
-    if (threadIdx.x == 0) arrivals = 0;
-    __syncthreads();
-
-    // ---- stage this warp's x slice: doubles [11*k0, 11*k0 + 1 + 11*(nk+1)) of the trajectory ----
-    const int k0 = 32 * warp;
-    const int nk = min(32, ts - k0);          // windows of this warp (>= 1)
-    const int cnt = 1 + PX * (nk + 1);        // slot 0 is x[11*k0] (dt for warp 0, unused otherwise)
-    const double *xs = xb + (size_t)PX * k0;  // even offset: 16-byte aligned whenever xb is
-    if ((reinterpret_cast<uintptr_t>(xs) & 15) == 0) {
-#pragma unroll
-        for (int it = 0; it < (SX_LEN / 2 + 31) / 32; it++) {
-            const int i = lane + 32 * it;
-            if (2 * i + 1 < cnt) st2(sx + 2 * i, __ldg(xs + 2 * i), __ldg(xs + 2 * i + 1));
-            else if (2 * i < cnt) sx[2 * i] = __ldg(xs + 2 * i);
-        }
-    } else {
-        for (int i = lane; i < cnt; i += 32) sx[i] = __ldg(xs + i);
-    }
-    const double dt = __ldg(xb);
-    __syncwarp();
-
     const int k = k0 + lane;
     const bool active = lane < nk;
     const double *s0 = sx + 1 + PX * (active ? lane : 0);
@@ -185,6 +152,81 @@ fg_batch_kernel(int slot, const double *__restrict__ x, long ldx, double *__rest
     const double gsg = c.g * sg, gcg = c.g * cg;
     const double n4 = W ? vz * bz - gcg : -gcg;  // (vx*bx + vy*by + vz*bz - g*cos(gam))
     const double Vadt = Va * dt, mdt = -dt;
+
+    // ---- objective terms: src/problemS10.cpp:246-258, 340-372; src/problemG7.cpp:240-241, 370 ----
+    sumT = 0.0, sump = 0.0;
+    {
+        const bool last_window = active && (k == ts - 1);  // also carries node ts
+        double r0x = 0.0, r0y = 0.0, rex = 0.0, rey = 0.0;
+        const double Te = s1[10];
+        if (active) sumT = T * T;
+        if (last_window) sumT += Te * Te;
+        if (S10) {
+            if (active) {
+                const double ddx = s0[0] - c.xg, ddy = s0[1] - c.yg;
+                const double r = sqrt(ddx * ddx + ddy * ddy);
+                const double rmR = r - c.rg;
+                sump = rmR * rmR;
+                r0x = c.kp * rmR * ddx / r;
+                r0y = c.kp * rmR * ddy / r;
+            }
+            if (last_window) {
+                const double ddx = s1[0] - c.xg, ddy = s1[1] - c.yg;
+                const double r = sqrt(ddx * ddx + ddy * ddy);
+                const double rmR = r - c.rg;
+                sump += rmR * rmR;
+                rex = c.kp * rmR * ddx / r;
+                rey = c.kp * rmR * ddy / r;
+            }
+            if (needG) {
+                // objective row [dt, (x, y, T) of every node]: this warp's 3*nk (+3) entries
+                if (active) {
+                    tile[3 * lane] = r0x;
+                    tile[3 * lane + 1] = r0y;
+                    tile[3 * lane + 2] = c.kT * T;
+                }
+                if (last_window) {
+                    tile[3 * lane + 3] = rex;
+                    tile[3 * lane + 4] = rey;
+                    tile[3 * lane + 5] = c.kT * Te;
+                }
+                __syncwarp();
+                const int cnt0 = 3 * nk + ((k0 + nk == ts) ? 3 : 0);
+                double *dst = Gb + 1 + 3 * k0;
+                for (int i = lane; i < cnt0; i += 32) dst[i] = tile[i];
+                __syncwarp();
+            }
+        } else if (needG) {
+            // G7 objective row [dt, x_0, y_0, T_0 .. T_{ts-1}, x_ts, y_ts, T_ts], src/problemG7.cpp:343-380
+            if (active) Gb[3 + k] = c.kT * T;
+            if (last_window) Gb[ts + 5] = c.kT * Te;
+        }
+    }
+
+    // ---- defects, src/problem.cpp:1003-1019 ----
+    if (needF) {
+        if (active) {
+            const double drag3 = (rSV * Va * CdT) / c.twomm;
+            const double dx3 = W ? Tmm - vz * az - gsg - drag3 : Tmm - gsg - drag3;
+            const double dx4 = (n4 + (CLrSV * Va * cp) / c.twomm) / Va;
+            const double lift5 = (CLrSV * Va * sp) / c.twomm;
+            const double dx5 = W ? -(vz * cz - lift5) / Vacg : -(-lift5) / Vacg;
+            double *f = tile + F_LD * lane;
+            st2(f + 0, s1[0] - vx * dt - s0[0], s1[1] - vy * dt - s0[1]);
+            st2(f + 2, s1[2] - vz * dt - s0[2], s1[3] - dx3 * dt - s0[3]);
+            st2(f + 4, s1[4] - dx4 * dt - s0[4], s1[5] - dx5 * dt - s0[5]);
+            st2(f + 6, s1[6] - dphi * dt - s0[6], s1[7] - dCL * dt - s0[7]);
+        }
+        __syncwarp();
+        double *dst = Fb + 1 + PF * k0;
+#pragma unroll
+        for (int it = 0; it < PF; it++) {
+            const int i = lane + 32 * it;  // i-th defect of the warp: window i/8, state i%8
+            if (i < PF * nk) dst[i] = tile[F_LD * (i >> 3) + (i & 7)];
+        }
+        __syncwarp();
+    }
+
 
     double *q = tile + QREC * lane;  // this lane's quarter record (stride 26 doubles: conflict-free)
     if (needG) {
@@ -300,108 +342,38 @@ fg_batch_kernel(int slot, const double *__restrict__ x, long ldx, double *__rest
         __syncwarp();
     }
 
-    // ---- objective terms: src/problemS10.cpp:246-258, 340-372; src/problemG7.cpp:240-241, 370 ----
-    double sumT = 0.0, sump = 0.0;
-    {
-        const bool last_window = active && (k == ts - 1);  // also carries node ts
-        double r0x = 0.0, r0y = 0.0, rex = 0.0, rey = 0.0;
-        const double Te = s1[10];
-        if (active) sumT = T * T;
-        if (last_window) sumT += Te * Te;
-        if (S10) {
-            if (active) {
-                const double ddx = s0[0] - c.xg, ddy = s0[1] - c.yg;
-                const double r = sqrt(ddx * ddx + ddy * ddy);
-                const double rmR = r - c.rg;
-                sump = rmR * rmR;
-                r0x = c.kp * rmR * ddx / r;
-                r0y = c.kp * rmR * ddy / r;
-            }
-            if (last_window) {
-                const double ddx = s1[0] - c.xg, ddy = s1[1] - c.yg;
-                const double r = sqrt(ddx * ddx + ddy * ddy);
-                const double rmR = r - c.rg;
-                sump += rmR * rmR;
-                rex = c.kp * rmR * ddx / r;
-                rey = c.kp * rmR * ddy / r;
-            }
-            if (needG) {
-                // objective row [dt, (x, y, T) of every node]: this warp's 3*nk (+3) entries
-                if (active) {
-                    tile[3 * lane] = r0x;
-                    tile[3 * lane + 1] = r0y;
-                    tile[3 * lane + 2] = c.kT * T;
-                }
-                if (last_window) {
-                    tile[3 * lane + 3] = rex;
-                    tile[3 * lane + 4] = rey;
-                    tile[3 * lane + 5] = c.kT * Te;
-                }
-                __syncwarp();
-                const int cnt0 = 3 * nk + ((k0 + nk == ts) ? 3 : 0);
-                double *dst = Gb + 1 + 3 * k0;
-                for (int i = lane; i < cnt0; i += 32) dst[i] = tile[i];
-                __syncwarp();
-            }
-        } else if (needG) {
-            // G7 objective row [dt, x_0, y_0, T_0 .. T_{ts-1}, x_ts, y_ts, T_ts], src/problemG7.cpp:343-380
-            if (active) Gb[3 + k] = c.kT * T;
-            if (last_window) Gb[ts + 5] = c.kT * Te;
-        }
-    }
+}
 
-    // ---- defects, src/problem.cpp:1003-1019 ----
-    if (needF) {
-        if (active) {
-            const double drag3 = (rSV * Va * CdT) / c.twomm;
-            const double dx3 = W ? Tmm - vz * az - gsg - drag3 : Tmm - gsg - drag3;
-            const double dx4 = (n4 + (CLrSV * Va * cp) / c.twomm) / Va;
-            const double lift5 = (CLrSV * Va * sp) / c.twomm;
-            const double dx5 = W ? -(vz * cz - lift5) / Vacg : -(-lift5) / Vacg;
-            double *f = tile + F_LD * lane;
-            st2(f + 0, s1[0] - vx * dt - s0[0], s1[1] - vy * dt - s0[1]);
-            st2(f + 2, s1[2] - vz * dt - s0[2], s1[3] - dx3 * dt - s0[3]);
-            st2(f + 4, s1[4] - dx4 * dt - s0[4], s1[5] - dx5 * dt - s0[5]);
-            st2(f + 6, s1[6] - dphi * dt - s0[6], s1[7] - dCL * dt - s0[7]);
-        }
-        __syncwarp();
-        double *dst = Fb + 1 + PF * k0;
-#pragma unroll
-        for (int it = 0; it < PF; it++) {
-            const int i = lane + 32 * it;  // i-th defect of the warp: window i/8, state i%8
-            if (i < PF * nk) dst[i] = tile[F_LD * (i >> 3) + (i & 7)];
-        }
-    }
+// Out-of-line instance for the persistent kernel: inlined into its trajectory/tile loop, ptxas keeps
+// ~60 extra doubles live across the loop and spills ~500 bytes per thread at the 128-register budget;
+// as a call the tile body is allocated on its own and does not spill.
+template <int FORM, int WIND>
+__device__ __noinline__ void tile_eval_call(const FgConst &c, const double *__restrict__ sx,
+                                            double *__restrict__ tile, const double dt, const int k0,
+                                            const int nk, const int lane, double *__restrict__ Fb,
+                                            double *__restrict__ Gb, const int needF, const int needG,
+                                            double &sumT, double &sump) {
+    tile_eval<FORM, WIND>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, sumT, sump);
+}
 
-    // ---- cost sums: warp shuffle, then across warps through shared memory ----
-    sumT = warp_sum(sumT);
-    if (S10) sump = warp_sum(sump);
-    int last = 0;
-    if (lane == 0) {
-        red[0][warp] = sumT;
-        red[1][warp] = sump;
-        __threadfence_block();
-        last = (atomicAdd(&arrivals, 1) == nwarps - 1);
-    }
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (!last) return;
-    __threadfence_block();
-
-    // ---- the last warp to arrive: F[0], boundary rows, objective-row ends ----
-    const volatile double *vred = &red[0][0];
-    double tT = 0.0, tp = 0.0;
-    for (int w = 0; w < nwarps; w++) {  // fixed order: deterministic
-        tT += vred[w];
-        tp += vred[32 + w];
-    }
-    const double *xe = xb + (size_t)PX * ts;  // node ts at xe[1..11], node 0 at xb[1..11]
+// ---- end of a trajectory: F[0], boundary rows, objective-row ends --------------------------------------
+//
+// Executed by one whole warp.  tT, tp: the trajectory's cost sums; n0 / ne: lane c < 11 holds state c of
+// node 0 / node ts.
+template <int FORM>
+__device__ __forceinline__ void traj_epilogue(const FgConst &c, const int lane, const double dt,
+                                              const double tT, const double tp, const double n0,
+                                              const double ne, double *__restrict__ Fb,
+                                              double *__restrict__ Gb, const int needF, const int needG) {
+    constexpr bool S10 = (FORM == TOLCUDA_FORM_S10);
+    const int ts = c.ts;
     double *Fbnd = Fb + (c.neF - c.nb);
     double *Gbnd = Gb + c.R0 + (size_t)REC * ts;
     if (S10) {
         if (needF) {
             if (lane == 0) Fb[0] = c.half_kT * tT + c.half_kp * tp + c.kdt * dt;  // src/problemS10.cpp:264
             if (lane < PX) {  // src/problemS10.cpp:292-303
-                double d = __ldg(xe + 1 + lane) - __ldg(xb + 1 + lane);
+                double d = ne - n0;
                 if (lane == 5) d = d - 2.0 * M_PI;
                 Fbnd[lane] = d;
             }
@@ -416,7 +388,8 @@ fg_batch_kernel(int slot, const double *__restrict__ x, long ldx, double *__rest
             }
         }
     } else {
-        const double x0 = __ldg(xb + 1), y0 = __ldg(xb + 2), xf = __ldg(xe + 1), yf = __ldg(xe + 2);
+        const double x0 = __shfl_sync(0xffffffffu, n0, 0), y0 = __shfl_sync(0xffffffffu, n0, 1);
+        const double xf = __shfl_sync(0xffffffffu, ne, 0), yf = __shfl_sync(0xffffffffu, ne, 1);
         const double ddx = xf - x0, ddy = yf - y0;
         const double dist = sqrt(ddx * ddx + ddy * ddy);
         if (needF) {
@@ -428,7 +401,7 @@ fg_batch_kernel(int slot, const double *__restrict__ x, long ldx, double *__rest
                 Fbnd[1] = ddy - dist * c.sin_chid;
                 Fbnd[11] = dist - dmax;
             }
-            if (lane >= 2 && lane < PX) Fbnd[lane] = __ldg(xe + 1 + lane) - __ldg(xb + 1 + lane);
+            if (lane >= 2 && lane < PX) Fbnd[lane] = ne - n0;
         }
         if (needG && lane == 0) {
             // objective row ends, src/problemG7.cpp:343-380 (sic: kp, where cost() uses kv)
@@ -458,55 +431,219 @@ fg_batch_kernel(int slot, const double *__restrict__ x, long ldx, double *__rest
     }
 }
 
+// ---- asynchronous global -> shared copies (LDGSTS) -------------------------------------------------------
+__device__ __forceinline__ void cp_async16(double *dst, const double *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async8(double *dst, const double *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// enqueue the copy of `cnt` doubles xs[0..cnt) into sx[0..cnt): 16-byte pieces when xs allows it
+__device__ __forceinline__ void slice_prefetch(double *sx, const double *xs, const int cnt, const int lane) {
+    if ((reinterpret_cast<uintptr_t>(xs) & 15) == 0) {
+#pragma unroll
+        for (int it = 0; it < (SX_LEN / 2 + 31) / 32; it++) {
+            const int i = lane + 32 * it;
+            if (2 * i + 1 < cnt) cp_async16(sx + 2 * i, xs + 2 * i);
+            else if (2 * i < cnt) cp_async8(sx + 2 * i, xs + 2 * i);
+        }
+    } else {
+        for (int i = lane; i < cnt; i += 32) cp_async8(sx + i, xs + i);
+    }
+}
+
+// ---- kernel A: one CTA per trajectory ------------------------------------------------------------------
+//
+// grid.x = B, blockDim.x = 32*ceil(ts/32) (<= MAXT).  Warp w owns windows 32w..32w+31 and runs on its
+// own after start-up; the cost sum crosses warps through shared memory and an arrival counter, and the
+// last warp to arrive runs the trajectory epilogue.  Best when B is small (down to the single
+// trajectory of the snOptA callback): all tiles of a trajectory proceed in parallel.
 template <int FORM, int WIND, int MAXT, int MINB>
-cudaError_t launch_one(const FgLaunch &L) {
-    auto kern = fg_batch_kernel<FORM, WIND, MAXT, MINB>;
-    const int nthr = 32 * ((L.ts + 31) / 32);
-    const size_t smem = sizeof(double) * (size_t)(nthr / 32) * WARP_SMEM;
+__global__ void __launch_bounds__(MAXT, MINB)
+fg_cta_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, long ldx, double *__restrict__ F, long ldF,
+              double *__restrict__ G, long ldG, int needF, int needG) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double red[2][32];
+    __shared__ int arrivals;
+    const int ts = c.ts;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    double *sx = smem + (size_t)warp * WARP_SMEM_A;
+    double *tile = sx + SX_LEN;
+    const size_t b = blockIdx.x;
+    const double *xb = x + b * ldx;
+    double *Fb = F + b * ldF;
+    double *Gb = G + b * ldG;
+
+    if (threadIdx.x == 0) arrivals = 0;
+    __syncthreads();
+
+    // stage this warp's x slice: doubles [11*k0, 11*k0 + 1 + 11*(nk+1)) of the trajectory
+    const int k0 = 32 * warp;
+    const int nk = min(32, ts - k0);
+    slice_prefetch(sx, xb + (size_t)PX * k0, 1 + PX * (nk + 1), lane);
+    cp_async_commit();
+    const double dt = __ldg(xb);
+    cp_async_wait<0>();
+    __syncwarp();
+
+    double sumT, sump;
+    tile_eval<FORM, WIND>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, sumT, sump);
+
+    // cost sums: warp shuffle, then across warps through shared memory
+    sumT = warp_sum(sumT);
+    if (FORM == TOLCUDA_FORM_S10) sump = warp_sum(sump);
+    int last = 0;
+    if (lane == 0) {
+        red[0][warp] = sumT;
+        red[1][warp] = sump;
+        __threadfence_block();
+        last = (atomicAdd(&arrivals, 1) == nwarps - 1);
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence_block();
+    const volatile double *vred = &red[0][0];
+    double tT = 0.0, tp = 0.0;
+    for (int w = 0; w < nwarps; w++) {  // fixed order: deterministic
+        tT += vred[w];
+        tp += vred[32 + w];
+    }
+    double n0 = 0.0, ne = 0.0;
+    if (lane < PX) {
+        n0 = __ldg(xb + 1 + lane);
+        ne = __ldg(xb + (size_t)PX * ts + 1 + lane);
+    }
+    traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG);
+}
+
+// ---- kernel B: persistent warps, one trajectory per warp at a time ------------------------------------------
+//
+// Every warp walks trajectories b = warp_id, warp_id + total_warps, ... and, within a trajectory, its
+// tiles in order, so cost sums stay in registers and no warp ever waits for another.  While a tile is
+// evaluated, the x slice of the next tile (or of the next trajectory's first tile) is already in flight
+// into the other half of a double buffer (cp.async), which hides the read latency behind the write
+// stream.  Best when B is large.
+template <int FORM, int WIND>
+__global__ void __launch_bounds__(WARPS_B * 32, MINB_B)
+fg_warp_kernel(const __grid_constant__ FgConst c, int B, const double *__restrict__ x, long ldx, double *__restrict__ F, long ldF,
+               double *__restrict__ G, long ldG, int needF, int needG) {
+    extern __shared__ __align__(16) double smem[];
+    const int ts = c.ts;
+    const int nt = (ts + 31) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *sxbuf = smem + (size_t)warp * WARP_SMEM_B;  // two x slices, then the tile
+    double *tile = sxbuf + 2 * SX_LEN;
+    const int total = gridDim.x * WARPS_B;
+    int b = blockIdx.x * WARPS_B + warp, t = 0, buf = 0;
+    if (b >= B) return;
+
+    slice_prefetch(sxbuf, x + (size_t)b * ldx, 1 + PX * (min(32, ts) + 1), lane);
+    cp_async_commit();
+    double dt = 0.0, n0 = 0.0, accT = 0.0, accp = 0.0;
+    while (b < B) {
+        int nb = b, ntile = t + 1;
+        if (ntile == nt) {
+            nb = b + total;
+            ntile = 0;
+        }
+        if (nb < B) {
+            const int nk2 = min(32, ts - 32 * ntile);
+            slice_prefetch(sxbuf + (buf ^ 1) * SX_LEN, x + (size_t)nb * ldx + (size_t)PX * 32 * ntile,
+                           1 + PX * (nk2 + 1), lane);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+
+        const double *sx = sxbuf + buf * SX_LEN;
+        const int k0 = 32 * t, nk = min(32, ts - k0);
+        if (t == 0) {
+            dt = sx[0];
+            n0 = lane < PX ? sx[1 + lane] : 0.0;
+        }
+        double *Fb = F + (size_t)b * ldF, *Gb = G + (size_t)b * ldG;
+        double sumT, sump;
+        tile_eval_call<FORM, WIND>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, sumT, sump);
+        accT += sumT;
+        accp += sump;
+        if (t == nt - 1) {
+            const double ne = lane < PX ? sx[1 + PX * nk + lane] : 0.0;
+            const double tT = warp_sum(accT);
+            const double tp = FORM == TOLCUDA_FORM_S10 ? warp_sum(accp) : 0.0;
+            traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG);
+            accT = accp = 0.0;
+        }
+        __syncwarp();  // every lane is done with sx before the next prefetch overwrites it
+        b = nb;
+        t = ntile;
+        buf ^= 1;
+    }
+    cp_async_wait<0>();
+}
+
+template <int FORM, int WIND, int MAXT, int MINB>
+cudaError_t launch_cta(const FgLaunch &L) {
+    auto kern = fg_cta_kernel<FORM, WIND, MAXT, MINB>;
+    const int nthr = 32 * ((L.c->ts + 31) / 32);
+    const size_t smem = sizeof(double) * (size_t)(nthr / 32) * WARP_SMEM_A;
     static size_t configured = 0;  // per instantiation
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    kern<<<L.B, nthr, smem, L.stream>>>(L.slot, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG);
+    kern<<<L.B, nthr, smem, L.stream>>>(*L.c, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG);
     return cudaGetLastError();
 }
 
 template <int FORM, int WIND>
-cudaError_t launch_npp(const FgLaunch &L) {
-    // register budget per block-size class: 65536 / (MAXT * MINB); L.minb picks a tuning variant
-    if (L.ts <= 128) {
-        if (L.minb == 4) return launch_one<FORM, WIND, 128, 4>(L);
-        if (L.minb == 6) return launch_one<FORM, WIND, 128, 6>(L);
-        return launch_one<FORM, WIND, 128, 5>(L);
+cudaError_t launch_warp(const FgLaunch &L) {
+    auto kern = fg_warp_kernel<FORM, WIND>;
+    const size_t smem = sizeof(double) * (size_t)WARPS_B * WARP_SMEM_B;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
     }
-    if (L.ts <= 256) {
-        if (L.minb == 3) return launch_one<FORM, WIND, 256, 3>(L);
-        return launch_one<FORM, WIND, 256, 2>(L);
-    }
-    if (L.ts <= 512) return launch_one<FORM, WIND, 512, 1>(L);
-    return launch_one<FORM, WIND, 1024, 1>(L);
+    const int resident = L.sm_count * MINB_B;  // persistent: one wave of CTAs
+    const int want = (L.B + WARPS_B - 1) / WARPS_B;
+    const int grid = want < resident ? want : resident;
+    kern<<<grid, WARPS_B * 32, smem, L.stream>>>(*L.c, L.B, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF,
+                                                 L.needG);
+    return cudaGetLastError();
+}
+
+template <int FORM, int WIND>
+cudaError_t launch_any(const FgLaunch &L) {
+    // kernel B needs enough trajectories to give every resident warp several; otherwise kernel A
+    // spreads the tiles of each trajectory over a CTA.  L.kernel forces one of them (tests, tuning).
+    const bool use_warp = L.kernel == 2 || (L.kernel == 0 && L.B >= 8 * L.sm_count * MINB_B * WARPS_B);
+    if (use_warp) return launch_warp<FORM, WIND>(L);
+    // register budget per block-size class: 65536 / (MAXT * MINB)
+    if (L.c->ts <= 128) return launch_cta<FORM, WIND, 128, 5>(L);
+    if (L.c->ts <= 256) return launch_cta<FORM, WIND, 256, 3>(L);
+    if (L.c->ts <= 512) return launch_cta<FORM, WIND, 512, 1>(L);
+    return launch_cta<FORM, WIND, 1024, 1>(L);
 }
 
 }  // namespace
 
-cudaError_t fg_upload_const(int slot, const FgConst &c, cudaStream_t stream) {
-    cudaError_t e = cudaMemcpyToSymbolAsync(c_fg, &c, sizeof(FgConst), sizeof(FgConst) * (size_t)slot,
-                                            cudaMemcpyHostToDevice, stream);
-    if (e != cudaSuccess) return e;
-    return cudaStreamSynchronize(stream);
-}
-
 cudaError_t fg_launch(const FgLaunch &L) {
     if (L.B <= 0) return cudaSuccess;
-    if (L.ts < 1 || L.ts > 1024) return cudaErrorInvalidValue;
-    if (L.form == TOLCUDA_FORM_S10) {
-        if (L.wind == 1) return launch_npp<TOLCUDA_FORM_S10, 1>(L);
-        if (L.wind == 0) return launch_npp<TOLCUDA_FORM_S10, 0>(L);
-    } else if (L.form == TOLCUDA_FORM_G7) {
-        if (L.wind == 1) return launch_npp<TOLCUDA_FORM_G7, 1>(L);
-        if (L.wind == 0) return launch_npp<TOLCUDA_FORM_G7, 0>(L);
+    if (!L.c || L.c->ts < 1 || L.c->ts > 1024) return cudaErrorInvalidValue;
+    if (L.c->form == TOLCUDA_FORM_S10) {
+        if (L.c->wind == 1) return launch_any<TOLCUDA_FORM_S10, 1>(L);
+        if (L.c->wind == 0) return launch_any<TOLCUDA_FORM_S10, 0>(L);
+    } else if (L.c->form == TOLCUDA_FORM_G7) {
+        if (L.c->wind == 1) return launch_any<TOLCUDA_FORM_G7, 1>(L);
+        if (L.c->wind == 0) return launch_any<TOLCUDA_FORM_G7, 0>(L);
     }
     return cudaErrorInvalidValue;
 }

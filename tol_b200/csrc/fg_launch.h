@@ -10,8 +10,7 @@
 #define TOLCUDA_FORM_S10 10
 
 struct FgLaunch {
-    int slot;  // index into the __constant__ FgConst table
-    int form, wind, ts, n, neF, R0;
+    const FgConst *c;  // the context's constants; passed by value as a __grid_constant__ parameter
     int B;
     const double *x;
     long ldx;
@@ -20,12 +19,10 @@ struct FgLaunch {
     double *G;
     long ldG;
     int needF, needG;
-    int minb; // tuning variant: minimum resident CTAs per SM the kernel is compiled for (0 = default)
+    int kernel;    // 0 = choose by batch size, 1 = kernel A (CTA per trajectory), 2 = kernel B (persistent warps)
+    int sm_count;  // SMs of the device
     cudaStream_t stream;
 };
-
-// copy one context's constants into its __constant__ slot (synchronises `stream`)
-cudaError_t fg_upload_const(int slot, const FgConst &c, cudaStream_t stream);
 
 // enqueue one batched F/G evaluation; device pointers
 cudaError_t fg_launch(const FgLaunch &L);

@@ -46,8 +46,8 @@ struct BatchLane {
 struct tolcuda_ctx {
     tolcuda_config cfg;
     FgConst c;
-    int slot = -1;
-    int minb = 0;
+    int kernel = 0;
+    int sm_count = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::vector<int> iG, jG;
     // single-trajectory path: pinned host staging + device buffers, allocated once
@@ -62,36 +62,19 @@ struct tolcuda_ctx {
 namespace {
 
 std::mutex g_mu;
-bool g_slot_used[TOLCUDA_MAX_CTX];
 tolcuda_ctx *g_bound = nullptr;
-
-int take_slot() {
-    std::lock_guard<std::mutex> lk(g_mu);
-    for (int i = 0; i < TOLCUDA_MAX_CTX; i++)
-        if (!g_slot_used[i]) {
-            g_slot_used[i] = true;
-            return i;
-        }
-    return -1;
-}
-
-void release_slot(int s) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (s >= 0) g_slot_used[s] = false;
-}
 
 long round_up(long v, long m) { return (v + m - 1) / m * m; }
 
 int launch(tolcuda_ctx *h, cudaStream_t st, int B, const double *x, long ldx, double *F, long ldF,
            double *G, long ldG, int needF, int needG) {
     FgLaunch L;
-    L.slot = h->slot;
-    L.form = h->c.form, L.wind = h->c.wind, L.ts = h->c.ts;
-    L.n = h->c.n, L.neF = h->c.neF, L.R0 = h->c.R0;
+    L.c = &h->c;
     L.B = B;
     L.x = x, L.ldx = ldx, L.F = F, L.ldF = ldF, L.G = G, L.ldG = ldG;
     L.needF = needF, L.needG = needG;
-    L.minb = h->minb;
+    L.kernel = h->kernel;
+    L.sm_count = h->sm_count;
     L.stream = st;
     cudaError_t e = fg_launch(L);
     if (e != cudaSuccess) return cuda_fail(e, "fg_launch");
@@ -198,23 +181,19 @@ int tolcuda_create(const tolcuda_config *cfg, tolcuda_handle *out) {
     }
     pattern_build(c.form, c.ts, h->iG, h->jG);
 
-    if (const char *env = std::getenv("TOLCUDA_MINB")) h->minb = std::atoi(env);
+    if (const char *env = std::getenv("TOLCUDA_KERNEL")) h->kernel = std::atoi(env);  // tests / tuning
 
     int rc = 0;
     do {
         cudaError_t e = cudaSetDevice(cfg->device);
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaSetDevice"); break; }
-        h->slot = take_slot();
-        if (h->slot < 0) {
-            set_error("too many live tolcuda contexts");
-            rc = TOLCUDA_ENOMEM;
-            break;
-        }
+        int sms = 0;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaDeviceGetAttribute"); break; }
+        h->sm_count = sms;
         e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaStreamCreate"); break; }
         h->stream = h->own_stream;
-        e = fg_upload_const(h->slot, c, h->stream);
-        if (e != cudaSuccess) { rc = cuda_fail(e, "constant upload"); break; }
         h->ox = 0;
         h->oF = tolcuda_padded_ld(c.n);
         h->oG = h->oF + tolcuda_padded_ld(c.neF);
@@ -281,7 +260,6 @@ int tolcuda_destroy(tolcuda_handle h) {
     if (h->h_one) cudaFreeHost(h->h_one);
     if (h->d_one) cudaFree(h->d_one);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
-    release_slot(h->slot);
     delete h;
     return 0;
 }

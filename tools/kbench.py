@@ -19,12 +19,12 @@ ap.add_argument("--workload", default="S10_tempest_ts200")
 ap.add_argument("--batch", type=int, default=16384)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
-ap.add_argument("--minb", type=int, default=0)
+ap.add_argument("--kernel", type=int, default=0)
 ap.add_argument("--need", default="FG")
 ap.add_argument("--distinct", type=int, default=512, help="distinct synthetic trajectories (tiled)")
 args = ap.parse_args()
-if args.minb:
-    os.environ["TOLCUDA_MINB"] = str(args.minb)
+if args.kernel:
+    os.environ["TOLCUDA_KERNEL"] = str(args.kernel)
 import tol_b200 as T  # noqa: E402
 from tol_b200.evaluator import padded_ld  # noqa: E402
 
@@ -54,6 +54,6 @@ with torch.cuda.stream(st):
     torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / args.steps
 by = 8.0 * B * (n + (neF if needF else 0) + (neG if needG else 0))
-print(json.dumps({"workload": args.workload, "B": B, "minb": args.minb, "need": args.need, "ms": ms,
+print(json.dumps({"workload": args.workload, "B": B, "kernel": args.kernel, "need": args.need, "ms": ms,
                   "node_evals_per_s": B * ts / (ms * 1e-3), "GBps": by / ms / 1e6,
                   "frac_of_6544": by / ms / 1e6 / 6544.0}))
