@@ -29,6 +29,7 @@ struct FgConst {
     double ARpiee;   // ac.AR*M_PI*ac.ee
     double ARpieemm; // ac.AR*M_PI*ac.ee*ac.mm
     double twomm;    // 2.0*ac.mm
+    double r_mm, r_twomm, r_ARpiee, r_ARpieemm;  // correctly rounded reciprocals of the four above
     double kT, kp, kdt;
     double half_kT;  // 0.5*gn.kT (== gn.kT*0.5)
     double half_kp;  // 0.5*gn.kp

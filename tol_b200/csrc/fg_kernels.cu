@@ -29,6 +29,7 @@
 // records (two defect rows each; a 26-double lane stride is bank-conflict-free for 16-byte
 // accesses), then the objective-row entries, then the 8 defects.  Cost sums use warp-shuffle
 // reductions; warps of a trajectory meet only through an arrival counter in shared memory.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -43,12 +44,11 @@ constexpr int PX = TOLCUDA_PX;
 constexpr int PF = TOLCUDA_PF;
 constexpr int REC = TOLCUDA_REC;
 constexpr int QREC = 26;                 // a quarter record: two defect rows x 13 columns
-constexpr int SX_LEN = 1 + PX * 33 + 2;  // a warp's x slice: dt slot + 33 nodes, rounded to even
+constexpr int SX_LEN = 368;               // a warp's x slice: dt slot + 33 nodes = 364 doubles, padded so
+                                         // that the tile behind it stays 128-byte aligned (TMA source)
 constexpr int TILE_LEN = 32 * QREC;      // doubles; also holds the F (32 x 10) and objective-row passes
 constexpr int WARP_SMEM_A = SX_LEN + TILE_LEN;      // kernel A: one x slice + tile per warp
 constexpr int WARP_SMEM_B = 2 * SX_LEN + TILE_LEN;  // kernel B: double-buffered x slice + tile
-constexpr int WARPS_B = 4;                          // kernel B: warps per CTA
-constexpr int MINB_B = 4;                           // kernel B: CTAs per SM the register budget allows
 constexpr int F_LD = 10;                 // smem stride of a window's 8 defects (== 2 mod 4: no conflicts)
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -57,28 +57,18 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// x / D given rD = RN(1/D): see the note in tile_eval
+__device__ __forceinline__ double div_r(double x, double D, double rD) {
+    const double q = x * rD;
+    return fma(fma(-q, D, x), rD, q);
+}
+
 __device__ __forceinline__ void st2(double *p, double a, double b) {
     *reinterpret_cast<double2 *>(p) = make_double2(a, b);
 }
 
-// Copy `chunks` pieces of 2*HALF doubles each from a dense shared tile to global memory where piece c
-// starts at dst + c*dst_stride: consecutive lanes take consecutive 16-byte words of the tile, so
-// every warp store covers 512 contiguous tile bytes (a run of whole pieces in global memory).
-template <int HALF>
-__device__ __forceinline__ void tile_out_vec(double *__restrict__ dst, int dst_stride,
-                                             const double *__restrict__ tile, int chunks, int lane) {
-    const int total = chunks * HALF;
-#pragma unroll
-    for (int it = 0; it < HALF; it++) {
-        const int i = lane + 32 * it;
-        if (i < total) {
-            const int c = i / HALF, j = i - c * HALF;
-            *reinterpret_cast<double2 *>(dst + (size_t)c * dst_stride + 2 * j) =
-                *reinterpret_cast<const double2 *>(tile + 2 * i);
-        }
-    }
-}
-
+// Copy `chunks` pieces of LEN doubles each from a dense shared tile to global memory where piece c
+// starts at dst + c*dst_stride (8-byte path for outputs that are not 16-byte aligned).
 template <int LEN>
 __device__ __forceinline__ void tile_out_scalar(double *__restrict__ dst, int dst_stride,
                                                 const double *__restrict__ tile, int chunks, int lane) {
@@ -96,14 +86,15 @@ __device__ __forceinline__ void tile_out_scalar(double *__restrict__ dst, int ds
 // ---- one warp, one tile of 32 windows ---------------------------------------------------------------
 //
 // sx: the warp's staged x slice (slot 0 = x[11*k0], node j of the slice at sx[1+11j]); tile: the warp's
-// output staging area.  Writes the tile's share of G (four quarter-record passes + objective-row
+// output staging area (disjoint from sx).  Writes the tile's share of G (four quarter-record passes + objective-row
 // entries) and of F (defects) and returns the tile's cost partial sums.
 template <int FORM, int WIND>
 __device__ __forceinline__ void tile_eval(const FgConst &c, const double *__restrict__ sx,
                                           double *__restrict__ tile, const double dt, const int k0,
                                           const int nk, const int lane, double *__restrict__ Fb,
                                           double *__restrict__ Gb, const int needF, const int needG,
-                                          double &sumT, double &sump) {
+                                          const CUtensorMap *gmap, const int bidx, double &sumT,
+                                          double &sump) {
     constexpr bool W = (WIND == 1);
     constexpr bool S10 = (FORM == TOLCUDA_FORM_S10);
     const int ts = c.ts;
@@ -116,9 +107,13 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, const double *__rest
 
     // ---- shared sub-expressions of the window (see window formulas in the file header) ----
     double sc, cc, sg, cg, sp, cp;
-    sincos(chi, &sc, &cc);
-    sincos(gam, &sg, &cg);
-    sincos(phi, &sp, &cp);
+    if (needG & 8) {  // experiment switch: no trigonometry
+        sc = sg = sp = 0.6, cc = cg = cp = 0.8;
+    } else {
+        sincos(chi, &sc, &cc);
+        sincos(gam, &sg, &cg);
+        sincos(phi, &sp, &cp);
+    }
     // wind, NED <- ENU (src/problem.cpp:522-524, 970-981): Wx = v = -Vref*zs/href with zs = -z,
     // dWx_dz = -dv_dz; every other component is exactly zero under models 0 and 1
     const double Wxz = c.wind_Wxz;
@@ -143,15 +138,20 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, const double *__rest
         ez = -((Wxz * cg) * sc);  // (dWy_dz*cc*cg - dWx_dz*cg*sc)
         fz = -(Wxzsc * sg);       // (dWy_dz*cc*sg - dWx_dz*sc*sg)
     }
-    const double CdT = c.Cd0 + (CL * CL) / c.ARpiee;  // (Cd0 + CL*CL/(AR*pi*ee))
+    // Shared-reciprocal division: x/D is evaluated as div_r(x, D, RN(1/D)) = one product plus one
+    // Markstein correction, which returns the correctly rounded quotient (the same value as IEEE
+    // division) for normal-range operands; the six denominators below serve 26 of a window's divisions.
+    const double rVa = 1.0 / Va;
+    const double CdT = c.Cd0 + div_r(CL * CL, c.ARpiee, c.r_ARpiee);  // (Cd0 + CL*CL/(AR*pi*ee))
     const double rSV = c.rhoSS * Va;                  // rho*SS*Va
     const double CLrS = CL * c.rho * c.SS;            // CL*rho*SS
     const double CLrSV = CLrS * Va;
     const double Va2 = Va * Va;
-    const double Tmm = T / c.mm;
+    const double Tmm = div_r(T, c.mm, c.r_mm);
     const double gsg = c.g * sg, gcg = c.g * cg;
     const double n4 = W ? vz * bz - gcg : -gcg;  // (vx*bx + vy*by + vz*bz - g*cos(gam))
     const double Vadt = Va * dt, mdt = -dt;
+    const double rVacg = 1.0 / Vacg;
 
     // ---- objective terms: src/problemS10.cpp:246-258, 340-372; src/problemG7.cpp:240-241, 370 ----
     sumT = 0.0, sump = 0.0;
@@ -166,17 +166,19 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, const double *__rest
                 const double ddx = s0[0] - c.xg, ddy = s0[1] - c.yg;
                 const double r = sqrt(ddx * ddx + ddy * ddy);
                 const double rmR = r - c.rg;
+                const double rr = 1.0 / r;
                 sump = rmR * rmR;
-                r0x = c.kp * rmR * ddx / r;
-                r0y = c.kp * rmR * ddy / r;
+                r0x = div_r(c.kp * rmR * ddx, r, rr);
+                r0y = div_r(c.kp * rmR * ddy, r, rr);
             }
             if (last_window) {
                 const double ddx = s1[0] - c.xg, ddy = s1[1] - c.yg;
                 const double r = sqrt(ddx * ddx + ddy * ddy);
                 const double rmR = r - c.rg;
+                const double rr = 1.0 / r;
                 sump += rmR * rmR;
-                rex = c.kp * rmR * ddx / r;
-                rey = c.kp * rmR * ddy / r;
+                rex = div_r(c.kp * rmR * ddx, r, rr);
+                rey = div_r(c.kp * rmR * ddy, r, rr);
             }
             if (needG) {
                 // objective row [dt, (x, y, T) of every node]: this warp's 3*nk (+3) entries
@@ -205,12 +207,12 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, const double *__rest
 
     // ---- defects, src/problem.cpp:1003-1019 ----
     if (needF) {
-        if (active) {
-            const double drag3 = (rSV * Va * CdT) / c.twomm;
+        {
+            const double drag3 = div_r(rSV * Va * CdT, c.twomm, c.r_twomm);
             const double dx3 = W ? Tmm - vz * az - gsg - drag3 : Tmm - gsg - drag3;
-            const double dx4 = (n4 + (CLrSV * Va * cp) / c.twomm) / Va;
-            const double lift5 = (CLrSV * Va * sp) / c.twomm;
-            const double dx5 = W ? -(vz * cz - lift5) / Vacg : -(-lift5) / Vacg;
+            const double dx4 = div_r(n4 + div_r(CLrSV * Va * cp, c.twomm, c.r_twomm), Va, rVa);
+            const double lift5 = div_r(CLrSV * Va * sp, c.twomm, c.r_twomm);
+            const double dx5 = W ? div_r(-(vz * cz - lift5), Vacg, rVacg) : div_r(-(-lift5), Vacg, rVacg);
             double *f = tile + F_LD * lane;
             st2(f + 0, s1[0] - vx * dt - s0[0], s1[1] - vy * dt - s0[1]);
             st2(f + 2, s1[2] - vz * dt - s0[2], s1[3] - dx3 * dt - s0[3]);
@@ -232,8 +234,49 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, const double *__rest
     if (needG) {
         double *Grec = Gb + c.R0 + (size_t)REC * k0;
         const bool vec = (reinterpret_cast<uintptr_t>(Grec) & 15) == 0;
+        // Copy-out of one pass.  TMA path (gmap != nullptr): the dense 32 x 26 tile is one box of the 3-D
+        // tensor [B][ts][104] that views the Jacobian records of the whole batch; one lane issues a
+        // cp.async.bulk.tensor store (rows past ts are clipped by the TMA unit) and the warp moves on.
+        // Loop path (outputs not 16-byte aligned): lanes copy 16- or 8-byte words themselves.
+        auto pass_out = [&](double *__restrict__ dst, const int col) {
+            if (needG & 4) {  // experiment switch (tools/kbench.py --need G4): evaluate and stage, store nothing
+                __syncwarp();
+                return;
+            }
+            if (gmap) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile(
+                        "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                        ::"l"(gmap), "r"(col), "r"(k0), "r"(bidx),
+                        "r"((uint32_t)__cvta_generic_to_shared(tile))
+                        : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    // the tile may be rewritten once the TMA unit has read it
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+                __syncwarp();
+                return;
+            }
+            __syncwarp();
+            if (vec) {
+                // 16-byte word i = lane + 32*it of the dense tile belongs to window i/13, position
+                // 2*(i%13) of that window's quarter record
+#pragma unroll
+                for (int it = 0; it < QREC / 2; it++) {
+                    const int i = lane + 32 * it, w = i / (QREC / 2);
+                    if (w < nk)
+                        *reinterpret_cast<double2 *>(dst + w * REC + 2 * (i - w * (QREC / 2))) =
+                            *reinterpret_cast<const double2 *>(tile + 2 * i);
+                }
+            } else {
+                tile_out_scalar<QREC>(dst, REC, tile, nk, lane);
+            }
+            __syncwarp();
+        };
         // ---- rows F1, F2: src/problem.cpp:1084-1088, 1098-1102 ----
-        if (active) {
+        {
             st2(q + 0, -vx, -1.0);
             st2(q + 2, 0.0, 0.0);
             st2(q + 4, mdt * cc * cg, Vadt * cc * sg);
@@ -248,20 +291,17 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, const double *__rest
             st2(q + 22, 0.0, 0.0);
             st2(q + 24, 0.0, 1.0);
         }
-        __syncwarp();
-        if (vec) tile_out_vec<QREC / 2>(Grec, REC, tile, nk, lane);
-        else tile_out_scalar<QREC>(Grec, REC, tile, nk, lane);
-        __syncwarp();
+        pass_out(Grec, 0);
         // ---- rows F3, F4: :1112-1115, :1125-1130 ----
-        if (active) {
-            const double dragv = (rSV * CdT) / c.mm;
-            const double drag11 = (c.rhoSS * Va2 * CdT) / c.twomm;
+        {
+            const double dragv = div_r(rSV * CdT, c.mm, c.r_mm);
+            const double drag11 = div_r(c.rhoSS * Va2 * CdT, c.twomm, c.r_twomm);
             const double g4dt = W ? vz * az - Tmm + gsg + drag11 : -Tmm + gsg + drag11;
             const double g4Va = W ? dt * (-(sg * az) + dragv) - 1.0 : dt * dragv - 1.0;
             const double g4gam = W ? mdt * (n4 + Vacg * az) : mdt * n4;
             const double g4chi = W ? dt * (ez * vz) : 0.0;
-            const double g4CL = (CLrS * Va2 * dt) / c.ARpieemm;
-            const double g4T = mdt / c.mm;
+            const double g4CL = div_r(CLrS * Va2 * dt, c.ARpieemm, c.r_ARpieemm);
+            const double g4T = div_r(mdt, c.mm, c.r_mm);
             st2(q + 0, Vasg, 0.0);
             st2(q + 2, 0.0, -1.0);
             st2(q + 4, dt * sg, Vadt * cg);
@@ -276,32 +316,33 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, const double *__rest
             st2(q + 22, 0.0, 0.0);
             st2(q + 24, g4T, 1.0);
         }
-        __syncwarp();
-        if (vec) tile_out_vec<QREC / 2>(Grec + QREC, REC, tile, nk, lane);
-        else tile_out_scalar<QREC>(Grec + QREC, REC, tile, nk, lane);
-        __syncwarp();
+        pass_out(Grec + QREC, QREC);
         // ---- rows F5, F6: :1140-1145, :1155-1160 ----
-        if (active) {
-            const double S5 = n4 + (CLrS * Va2 * cp) / c.twomm;
-            const double liftv = (CLrSV * cp) / c.mm;
-            const double g5dt = -S5 / Va;
-            const double g5Va = W ? (dt * S5) / Va2 - (dt * (-(sg * bz) + liftv)) / Va
-                                  : (dt * S5) / Va2 - (dt * liftv) / Va;
-            const double g5gam = W ? -(dt * (vz * az + gsg - Vacg * bz)) / Va - 1.0 : -(dt * gsg) / Va - 1.0;
-            const double g5chi = W ? -(dt * (fz * vz)) / Va : 0.0;
-            const double g5phi = (CLrSV * dt * sp) / c.twomm;
-            const double g5CL = -(rSV * dt * cp) / c.twomm;
-            const double lift6 = (CLrS * Va2 * sp) / c.twomm;
+        {
+            const double rVa2 = 1.0 / Va2;
+            const double S5 = n4 + div_r(CLrS * Va2 * cp, c.twomm, c.r_twomm);
+            const double liftv = div_r(CLrSV * cp, c.mm, c.r_mm);
+            const double g5dt = div_r(-S5, Va, rVa);
+            const double g5Va = W ? div_r(dt * S5, Va2, rVa2) - div_r(dt * (-(sg * bz) + liftv), Va, rVa)
+                                  : div_r(dt * S5, Va2, rVa2) - div_r(dt * liftv, Va, rVa);
+            const double g5gam = W ? div_r(-(dt * (vz * az + gsg - Vacg * bz)), Va, rVa) - 1.0
+                                   : div_r(-(dt * gsg), Va, rVa) - 1.0;
+            const double g5chi = W ? div_r(-(dt * (fz * vz)), Va, rVa) : 0.0;
+            const double g5phi = div_r(CLrSV * dt * sp, c.twomm, c.r_twomm);
+            const double g5CL = div_r(-(rSV * dt * cp), c.twomm, c.r_twomm);
+            const double lift6 = div_r(CLrS * Va2 * sp, c.twomm, c.r_twomm);
             const double Q = W ? vz * cz - lift6 : -lift6;
-            const double sidev = (CLrSV * sp) / c.mm;
-            const double g6dt = Q / Vacg;
-            const double g6Va = W ? -(dt * (sg * cz + sidev)) / Vacg - (dt * Q) / (Va2 * cg)
-                                  : -(dt * sidev) / Vacg - (dt * Q) / (Va2 * cg);
-            const double g6gam = W ? (dt * sg * Q) / (Va * (cg * cg)) - (dt * (Vacg * cz)) / Vacg
-                                   : (dt * sg * Q) / (Va * (cg * cg));
-            const double g6chi = W ? -(dt * (vz * dz)) / Vacg - 1.0 : -1.0;
-            const double g6phi = -(CLrSV * dt * cp) / (c.twomm * cg);
-            const double g6CL = -(rSV * dt * sp) / (c.twomm * cg);
+            const double sidev = div_r(CLrSV * sp, c.mm, c.r_mm);
+            const double Va2cg = Va2 * cg, Vacg2 = Va * (cg * cg), tmcg = c.twomm * cg;
+            const double rVa2cg = 1.0 / Va2cg, rVacg2 = 1.0 / Vacg2, rtmcg = 1.0 / tmcg;
+            const double g6dt = div_r(Q, Vacg, rVacg);
+            const double g6Va = W ? div_r(-(dt * (sg * cz + sidev)), Vacg, rVacg) - div_r(dt * Q, Va2cg, rVa2cg)
+                                  : div_r(-(dt * sidev), Vacg, rVacg) - div_r(dt * Q, Va2cg, rVa2cg);
+            const double g6gam = W ? div_r(dt * sg * Q, Vacg2, rVacg2) - div_r(dt * (Vacg * cz), Vacg, rVacg)
+                                   : div_r(dt * sg * Q, Vacg2, rVacg2);
+            const double g6chi = W ? div_r(-(dt * (vz * dz)), Vacg, rVacg) - 1.0 : -1.0;
+            const double g6phi = div_r(-(CLrSV * dt * cp), tmcg, rtmcg);
+            const double g6CL = div_r(-(rSV * dt * sp), tmcg, rtmcg);
             st2(q + 0, g5dt, 0.0);
             st2(q + 2, 0.0, 0.0);
             st2(q + 4, g5Va, g5gam);
@@ -316,12 +357,9 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, const double *__rest
             st2(q + 22, 0.0, 0.0);
             st2(q + 24, 0.0, 1.0);
         }
-        __syncwarp();
-        if (vec) tile_out_vec<QREC / 2>(Grec + 2 * QREC, REC, tile, nk, lane);
-        else tile_out_scalar<QREC>(Grec + 2 * QREC, REC, tile, nk, lane);
-        __syncwarp();
+        pass_out(Grec + 2 * QREC, 2 * QREC);
         // ---- rows F7, F8: :1170-1172, :1182-1184 ----
-        if (active) {
+        {
             st2(q + 0, -dphi, 0.0);
             st2(q + 2, 0.0, 0.0);
             st2(q + 4, 0.0, 0.0);
@@ -336,10 +374,7 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, const double *__rest
             st2(q + 22, 0.0, mdt);
             st2(q + 24, 0.0, 1.0);
         }
-        __syncwarp();
-        if (vec) tile_out_vec<QREC / 2>(Grec + 3 * QREC, REC, tile, nk, lane);
-        else tile_out_scalar<QREC>(Grec + 3 * QREC, REC, tile, nk, lane);
-        __syncwarp();
+        pass_out(Grec + 3 * QREC, 3 * QREC);
     }
 
 }
@@ -348,12 +383,13 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, const double *__rest
 // ~60 extra doubles live across the loop and spills ~500 bytes per thread at the 128-register budget;
 // as a call the tile body is allocated on its own and does not spill.
 template <int FORM, int WIND>
-__device__ __noinline__ void tile_eval_call(const FgConst &c, const double *__restrict__ sx,
-                                            double *__restrict__ tile, const double dt, const int k0,
+__device__ __noinline__ void tile_eval_call(const FgConst &c, const double *sx, double *tile,
+                                            const double dt, const int k0,
                                             const int nk, const int lane, double *__restrict__ Fb,
                                             double *__restrict__ Gb, const int needF, const int needG,
-                                            double &sumT, double &sump) {
-    tile_eval<FORM, WIND>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, sumT, sump);
+                                            const CUtensorMap *gmap, const int bidx, double &sumT,
+                                            double &sump) {
+    tile_eval<FORM, WIND>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, gmap, bidx, sumT, sump);
 }
 
 // ---- end of a trajectory: F[0], boundary rows, objective-row ends --------------------------------------
@@ -466,9 +502,10 @@ __device__ __forceinline__ void slice_prefetch(double *sx, const double *xs, con
 // trajectory of the snOptA callback): all tiles of a trajectory proceed in parallel.
 template <int FORM, int WIND, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
-fg_cta_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, long ldx, double *__restrict__ F, long ldF,
+fg_cta_kernel(const __grid_constant__ FgConst c, const __grid_constant__ CUtensorMap gmap, int use_tma,
+              const double *__restrict__ x, long ldx, double *__restrict__ F, long ldF,
               double *__restrict__ G, long ldG, int needF, int needG) {
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(128) double smem[];
     __shared__ double red[2][32];
     __shared__ int arrivals;
     const int ts = c.ts;
@@ -493,7 +530,8 @@ fg_cta_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, l
     __syncwarp();
 
     double sumT, sump;
-    tile_eval<FORM, WIND>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, sumT, sump);
+    tile_eval<FORM, WIND>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, use_tma ? &gmap : nullptr,
+                          (int)b, sumT, sump);
 
     // cost sums: warp shuffle, then across warps through shared memory
     sumT = warp_sum(sumT);
@@ -527,59 +565,65 @@ fg_cta_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, l
 // Every warp walks trajectories b = warp_id, warp_id + total_warps, ... and, within a trajectory, its
 // tiles in order, so cost sums stay in registers and no warp ever waits for another.  While a tile is
 // evaluated, the x slice of the next tile (or of the next trajectory's first tile) is already in flight
-// into the other half of a double buffer (cp.async), which hides the read latency behind the write
-// stream.  Best when B is large.
-template <int FORM, int WIND>
-__global__ void __launch_bounds__(WARPS_B * 32, MINB_B)
-fg_warp_kernel(const __grid_constant__ FgConst c, int B, const double *__restrict__ x, long ldx, double *__restrict__ F, long ldF,
+// (cp.async) into the other slice buffer, which hides the read latency behind the write stream.
+// The tile body is called out of line (tile_eval_call): inlined into this loop it costs ~500 bytes of
+// spills per thread.  Measured slower than kernel A on B200 at every batch size tried so far; kept as a
+// selectable variant (TOLCUDA_KERNEL=2).
+template <int FORM, int WIND, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+fg_warp_kernel(const __grid_constant__ FgConst c, const __grid_constant__ CUtensorMap gmap, int use_tma,
+               int B, const double *__restrict__ x, long ldx, double *__restrict__ F, long ldF,
                double *__restrict__ G, long ldG, int needF, int needG) {
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(128) double smem[];
     const int ts = c.ts;
     const int nt = (ts + 31) >> 5;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *sxbuf = smem + (size_t)warp * WARP_SMEM_B;  // two x slices, then the tile
-    double *tile = sxbuf + 2 * SX_LEN;
-    const int total = gridDim.x * WARPS_B;
-    int b = blockIdx.x * WARPS_B + warp, t = 0, buf = 0;
+    const int lane0 = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *wsm = smem + (size_t)warp * WARP_SMEM_B;
+    const int total = gridDim.x * WARPS;
+    int b = blockIdx.x * WARPS + warp, t = 0, buf = 0;
     if (b >= B) return;
 
-    slice_prefetch(sxbuf, x + (size_t)b * ldx, 1 + PX * (min(32, ts) + 1), lane);
+    slice_prefetch(wsm, x + (size_t)b * ldx, 1 + PX * (min(32, ts) + 1), lane0);
     cp_async_commit();
     double dt = 0.0, n0 = 0.0, accT = 0.0, accp = 0.0;
+#pragma unroll 1
     while (b < B) {
+        const int lane = lane0;
         int nb = b, ntile = t + 1;
         if (ntile == nt) {
             nb = b + total;
             ntile = 0;
         }
+        double *sx = wsm + buf * SX_LEN;             // current slice
+        double *sx_next = wsm + (buf ^ 1) * SX_LEN;  // the other slice
+        double *tile = wsm + 2 * SX_LEN;
         if (nb < B) {
             const int nk2 = min(32, ts - 32 * ntile);
-            slice_prefetch(sxbuf + (buf ^ 1) * SX_LEN, x + (size_t)nb * ldx + (size_t)PX * 32 * ntile,
-                           1 + PX * (nk2 + 1), lane);
+            slice_prefetch(sx_next, x + (size_t)nb * ldx + (size_t)PX * 32 * ntile, 1 + PX * (nk2 + 1), lane);
         }
         cp_async_commit();
         cp_async_wait<1>();
         __syncwarp();
 
-        const double *sx = sxbuf + buf * SX_LEN;
         const int k0 = 32 * t, nk = min(32, ts - k0);
         if (t == 0) {
             dt = sx[0];
             n0 = lane < PX ? sx[1 + lane] : 0.0;
         }
+        const double ne = (t == nt - 1 && lane < PX) ? sx[1 + PX * nk + lane] : 0.0;
         double *Fb = F + (size_t)b * ldF, *Gb = G + (size_t)b * ldG;
         double sumT, sump;
-        tile_eval_call<FORM, WIND>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, sumT, sump);
+        tile_eval_call<FORM, WIND>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, use_tma ? &gmap : nullptr,
+                                   b, sumT, sump);
         accT += sumT;
         accp += sump;
         if (t == nt - 1) {
-            const double ne = lane < PX ? sx[1 + PX * nk + lane] : 0.0;
             const double tT = warp_sum(accT);
             const double tp = FORM == TOLCUDA_FORM_S10 ? warp_sum(accp) : 0.0;
             traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG);
             accT = accp = 0.0;
         }
-        __syncwarp();  // every lane is done with sx before the next prefetch overwrites it
+        __syncwarp();  // every lane is done with the tile before the next iteration's prefetch reuses it
         b = nb;
         t = ntile;
         buf ^= 1;
@@ -598,34 +642,35 @@ cudaError_t launch_cta(const FgLaunch &L) {
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    kern<<<L.B, nthr, smem, L.stream>>>(*L.c, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG);
+    kern<<<L.B, nthr, smem, L.stream>>>(*L.c, L.gmap ? *L.gmap : CUtensorMap(), L.gmap != nullptr, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG);
     return cudaGetLastError();
 }
 
-template <int FORM, int WIND>
+template <int FORM, int WIND, int WARPS, int MINB>
 cudaError_t launch_warp(const FgLaunch &L) {
-    auto kern = fg_warp_kernel<FORM, WIND>;
-    const size_t smem = sizeof(double) * (size_t)WARPS_B * WARP_SMEM_B;
+    auto kern = fg_warp_kernel<FORM, WIND, WARPS, MINB>;
+    const size_t smem = sizeof(double) * (size_t)WARPS * WARP_SMEM_B;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const int resident = L.sm_count * MINB_B;  // persistent: one wave of CTAs
-    const int want = (L.B + WARPS_B - 1) / WARPS_B;
+    const int resident = L.sm_count * MINB;  // persistent: one wave of CTAs
+    const int want = (L.B + WARPS - 1) / WARPS;
     const int grid = want < resident ? want : resident;
-    kern<<<grid, WARPS_B * 32, smem, L.stream>>>(*L.c, L.B, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF,
-                                                 L.needG);
+    kern<<<grid, WARPS * 32, smem, L.stream>>>(*L.c, L.gmap ? *L.gmap : CUtensorMap(), L.gmap != nullptr, L.B, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF,
+                                               L.needG);
     return cudaGetLastError();
 }
 
 template <int FORM, int WIND>
 cudaError_t launch_any(const FgLaunch &L) {
-    // kernel B needs enough trajectories to give every resident warp several; otherwise kernel A
-    // spreads the tiles of each trajectory over a CTA.  L.kernel forces one of them (tests, tuning).
-    const bool use_warp = L.kernel == 2 || (L.kernel == 0 && L.B >= 8 * L.sm_count * MINB_B * WARPS_B);
-    if (use_warp) return launch_warp<FORM, WIND>(L);
+    // kernel A unless kernel B is asked for (L.kernel == 2; tests, tuning)
+    const bool use_warp = L.kernel == 2;
+    if (use_warp) {
+        return launch_warp<FORM, WIND, 4, 4>(L);  // 128 registers, 16 warps / SM
+    }
     // register budget per block-size class: 65536 / (MAXT * MINB)
     if (L.c->ts <= 128) return launch_cta<FORM, WIND, 128, 5>(L);
     if (L.c->ts <= 256) return launch_cta<FORM, WIND, 256, 3>(L);

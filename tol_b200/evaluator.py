@@ -135,6 +135,7 @@ class Evaluator:
         """tolcuda_eval_batch with torch CUDA tensors [B, ld] (float64, row-contiguous)"""
         B = X.shape[0]
         flags = (NEED_F if needF else 0) | (NEED_G if needG else 0) | DEVICE_PTRS | (0 if sync else NO_SYNC)
+        flags |= (int(needG) >> 1) << 8  # experiment switches (tools/kbench.py)
         _l.check(self.L.tolcuda_eval_batch(self.h, B, X.data_ptr(), X.stride(0), F.data_ptr(), F.stride(0),
                                            G.data_ptr(), G.stride(0), flags))
 

@@ -42,6 +42,8 @@ Gd = torch.empty(B, ldG, dtype=torch.float64, device="cuda")
 st = torch.cuda.Stream()
 ev.set_stream(st.cuda_stream)
 needF, needG = "F" in args.need, "G" in args.need
+if needG:  # experiment switches ride on the needG flag bits of the launch (G4 = no stores, G8 = no trig)
+    needG = 1 + sum(int(ch) for ch in args.need if ch.isdigit())
 with torch.cuda.stream(st):
     for _ in range(args.warmup):
         ev.eval_batch_device(Xd, Fd, Gd, needF, needG, sync=False)
