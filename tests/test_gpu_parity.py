@@ -107,13 +107,12 @@ def test_batch_host_pointers_chunked(name, monkeypatch):
 
 @pytest.mark.parametrize("name,seed0", [("G7_skywalker_ts100", T.synth.SEED_G7),
                                         ("S10_tempest_ts200", T.synth.SEED_S10)])
-@pytest.mark.parametrize("kernel", [1, 2])
-@pytest.mark.parametrize("no_tma", [0, 1])
-def test_section_8d_batches_against_oracle(name, seed0, kernel, no_tma, monkeypatch, oracle_built):
-    """configs 3 and 4 of BASELINE.json on a 64-trajectory subset, through both kernels (CTA per
-    trajectory / persistent warps) and both copy-out paths (TMA tensor store / lane copies)"""
+@pytest.mark.parametrize("kernel", [1, 2, 3])
+def test_section_8d_batches_against_oracle(name, seed0, kernel, monkeypatch, oracle_built):
+    """configs 3 and 4 of BASELINE.json on a 64-trajectory subset, through every kernel variant (CTA per
+    trajectory at two register budgets / persistent warps); the lane-copy fallback of the TMA bulk
+    stores is exercised by the odd-leading-dimension cases of test_batch_device_pointers"""
     monkeypatch.setenv("TOLCUDA_KERNEL", str(kernel))
-    monkeypatch.setenv("TOLCUDA_NO_TMA", str(no_tma))
     g = load_golden(name)
     p = port_from_golden(g)
     B = 64

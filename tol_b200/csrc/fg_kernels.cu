@@ -10,26 +10,32 @@
 //   problemS10::{cost,boundaryConstraints,costGradient,boundaryGradients}  src/problemS10.cpp:227-415
 //   problemG7::{cost,boundaryConstraints,costGradient,boundaryGradients}   src/problemG7.cpp:225-513
 //
-// Work decomposition.  One CTA owns one trajectory; one thread owns one collocation window k (node k
-// and the 8 states of node k+1).  The reference instead walks the neG coordinate entries and, for
-// every single entry, re-evaluates the whole 12-column expression table of that entry's row
-// (src/problem.cpp:785-802, 1074-1199); here every parenthesised sub-expression is evaluated once
-// per node.
+// Work decomposition.  One thread owns one collocation window k (node k and the 8 states of node
+// k+1); one warp owns a tile of 32 consecutive windows of one trajectory and runs on its own.  The
+// reference instead walks the neG coordinate entries and, for every single entry, re-evaluates the
+// whole 12-column expression table of that entry's row (src/problem.cpp:785-802, 1074-1199); here
+// every parenthesised sub-expression is evaluated once per node.
 //
 // Numerics.  Compiled with -fmad=false: every product and sum is rounded separately, in the C
 // left-to-right association of the cited reference line, exactly like the reference's x86-64 -O2
 // build (no FMA contraction).  Sub-expressions the reference multiplies by a wind-gradient
 // component that is identically zero under the selected wind model are dropped: x + 0*y == x
-// for finite y, so this changes no value (only, possibly, the sign of a zero).  What is left to
+// for finite y, so this changes no value (only, possibly, the sign of a zero).  Divisions by a
+// denominator that occurs several times share one correctly rounded reciprocal and a Markstein
+// correction (div_r), which yields the IEEE quotient for normal-range operands.  What is left to
 // differ from the reference is the last-ulp behaviour of sin/cos (CUDA libdevice vs glibc).
 //
-// Memory.  Each warp stages the 33-node slice of x its 32 windows need in shared memory with
-// coalesced 16-byte loads, and every output leaves through the warp's shared tile as coalesced
-// 16-byte stores: the 104-value Jacobian record of a window goes out as four 26-value quarter
-// records (two defect rows each; a 26-double lane stride is bank-conflict-free for 16-byte
-// accesses), then the objective-row entries, then the 8 defects.  Cost sums use warp-shuffle
-// reductions; warps of a trajectory meet only through an arrival counter in shared memory.
-#include <cuda.h>
+// Memory.  The kernel is bound by its write stream (G is 91 % of the bytes), and on B200 that stream
+// is limited by L2 write REQUESTS, not bytes: pieces smaller than whole 128-byte lines cost bandwidth
+// (208-byte pieces measured 4.8 TB/s against 7.5 TB/s for a plain fill).  So G leaves as whole
+// 832-byte window records, contiguous in SNOPT coordinate order:
+//   * each warp stages the 33-node slice of x its windows need in shared memory (cp.async, 16-byte);
+//   * a window's 104-value record is assembled in a per-warp tile of 8 record slots whose structural
+//     constants (0, +-1) are written once; per group of 8 windows only the 33 x-dependent entries are
+//     stored (lane stride 106 doubles: conflict-free), and each lane then hands its finished record to
+//     the TMA unit as one cp.async.bulk shared->global copy;
+//   * F (8 defects per window) and the S10 objective-row entries go out through the dead x slice as
+//     coalesced stores.  Cost sums use warp-shuffle reductions.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -37,19 +43,20 @@
 #include "fg_const.h"
 #include "fg_launch.h"
 
-
 namespace {
 
 constexpr int PX = TOLCUDA_PX;
 constexpr int PF = TOLCUDA_PF;
 constexpr int REC = TOLCUDA_REC;
-constexpr int QREC = 26;                 // a quarter record: two defect rows x 13 columns
-constexpr int SX_LEN = 368;               // a warp's x slice: dt slot + 33 nodes = 364 doubles, padded so
-                                         // that the tile behind it stays 128-byte aligned (TMA source)
-constexpr int TILE_LEN = 32 * QREC;      // doubles; also holds the F (32 x 10) and objective-row passes
-constexpr int WARP_SMEM_A = SX_LEN + TILE_LEN;      // kernel A: one x slice + tile per warp
-constexpr int WARP_SMEM_B = 2 * SX_LEN + TILE_LEN;  // kernel B: double-buffered x slice + tile
-constexpr int F_LD = 10;                 // smem stride of a window's 8 defects (== 2 mod 4: no conflicts)
+constexpr int REC_LD = 106;            // smem stride of a record slot: 16-byte aligned and == 2 (mod 4), so
+                                       // 8-/16-byte stores of consecutive lanes fall in distinct banks
+constexpr int NPP = 8;                 // record slots per warp tile = windows drained per group
+constexpr int SX_LEN = 368;            // a warp's x slice: slot for x[11*k0] + 33 nodes = 364 doubles
+constexpr int TILE_LEN = NPP * REC_LD; // 848 doubles
+constexpr int WARP_SMEM = SX_LEN + TILE_LEN;        // kernel A
+constexpr int WARP_SMEM_B = 2 * SX_LEN + TILE_LEN;  // kernel B: double-buffered x slice
+constexpr int F_LD = 10;               // smem stride of a window's 8 defects (== 2 mod 4)
+constexpr int NVAR = 31;               // x-dependent entries of a record (plus two -dt entries)
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -57,7 +64,7 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// x / D given rD = RN(1/D): see the note in tile_eval
+// x / D given rD = RN(1/D): one product plus one Markstein correction
 __device__ __forceinline__ double div_r(double x, double D, double rD) {
     const double q = x * rD;
     return fma(fma(-q, D, x), rD, q);
@@ -67,47 +74,114 @@ __device__ __forceinline__ void st2(double *p, double a, double b) {
     *reinterpret_cast<double2 *>(p) = make_double2(a, b);
 }
 
-// Copy `chunks` pieces of LEN doubles each from a dense shared tile to global memory where piece c
-// starts at dst + c*dst_stride (8-byte path for outputs that are not 16-byte aligned).
-template <int LEN>
-__device__ __forceinline__ void tile_out_scalar(double *__restrict__ dst, int dst_stride,
-                                                const double *__restrict__ tile, int chunks, int lane) {
-    const int total = chunks * LEN;
+// ---- asynchronous copies ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(double *dst, const double *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async8(double *dst, const double *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// enqueue the copy of `cnt` doubles xs[0..cnt) into sx[0..cnt): 16-byte pieces when xs allows it
+__device__ __forceinline__ void slice_prefetch(double *sx, const double *xs, const int cnt, const int lane) {
+    if ((reinterpret_cast<uintptr_t>(xs) & 15) == 0) {
 #pragma unroll
-    for (int it = 0; it < LEN; it++) {
-        const int i = lane + 32 * it;
-        if (i < total) {
-            const int c = i / LEN, j = i - c * LEN;
-            dst[(size_t)c * dst_stride + j] = tile[i];
+        for (int it = 0; it < (SX_LEN / 2 + 31) / 32; it++) {
+            const int i = lane + 32 * it;
+            if (2 * i + 1 < cnt) cp_async16(sx + 2 * i, xs + 2 * i);
+            else if (2 * i < cnt) cp_async8(sx + 2 * i, xs + 2 * i);
         }
+    } else {
+        for (int i = lane; i < cnt; i += 32) cp_async8(sx + i, xs + i);
     }
+}
+
+// TMA bulk copy shared -> global of one record (832 bytes, both sides 16-byte aligned)
+__device__ __forceinline__ void bulk_store_record(double *gdst, const double *ssrc) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "n"(REC * 8)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ---- record slots -------------------------------------------------------------------------------------
+//
+// Record layout (row s of the window at 13*s: [d/d dt, d/d c0..c10 @k, d/d c_s @k+1]).  Structural
+// constants: tabG zero-initialisation and the +-1 entries (src/problem.cpp:1038, 1084, 1098, 1112, 1170,
+// 1182, 1204); everything x-dependent is zeroed here and written per window by record_store.
+__device__ __forceinline__ void record_init(double *rec) {
+#pragma unroll
+    for (int j = 0; j < REC; j += 2) st2(rec + j, 0.0, 0.0);
+    rec[1] = -1.0;   // F1 d/dx
+    rec[15] = -1.0;  // F2 d/dy
+    rec[29] = -1.0;  // F3 d/dz
+    rec[85] = -1.0;  // F7 d/dphi
+    rec[99] = -1.0;  // F8 d/dCL
+#pragma unroll
+    for (int s = 0; s < PF; s++) rec[13 * s + 12] = 1.0;  // d/d(state s at node k+1)
+}
+
+// the x-dependent entries; adjacent (even, odd) positions leave as one 16-byte store
+__device__ __forceinline__ void record_store(double *rec, const double *v, const double mdt) {
+    rec[0] = v[0];  // F1: dt | Va, gam | chi          src/problem.cpp:1084-1088
+    st2(rec + 4, v[1], v[2]);
+    rec[6] = v[3];
+    rec[13] = v[4];  // F2                              :1098-1102
+    rec[17] = v[5];
+    st2(rec + 18, v[6], v[7]);
+    rec[26] = v[8];  // F3: dt | Va, gam                :1112-1115
+    st2(rec + 30, v[9], v[10]);
+    rec[39] = v[11];  // F4: dt | Va | gam, chi | CL | T :1125-1130
+    rec[43] = v[12];
+    st2(rec + 44, v[13], v[14]);
+    rec[47] = v[15];
+    rec[50] = v[16];
+    rec[52] = v[17];  // F5: dt | Va, gam | chi, phi | CL :1140-1145
+    st2(rec + 56, v[18], v[19]);
+    st2(rec + 58, v[20], v[21]);
+    rec[60] = v[22];
+    rec[65] = v[23];  // F6                              :1155-1160
+    rec[69] = v[24];
+    st2(rec + 70, v[25], v[26]);
+    st2(rec + 72, v[27], v[28]);
+    rec[78] = v[29];  // F7: dt, d/ddphi = -dt           :1171-1172
+    st2(rec + 86, 0.0, mdt);
+    rec[91] = v[30];  // F8: dt, d/ddCL = -dt            :1183-1184
+    st2(rec + 100, 0.0, mdt);
 }
 
 // ---- one warp, one tile of 32 windows ---------------------------------------------------------------
 //
-// sx: the warp's staged x slice (slot 0 = x[11*k0], node j of the slice at sx[1+11j]); tile: the warp's
-// output staging area (disjoint from sx).  Writes the tile's share of G (four quarter-record passes + objective-row
-// entries) and of F (defects) and returns the tile's cost partial sums.
+// sx: the warp's staged x slice (slot 0 = x[11*k0], node j of the slice at sx[1+11j]).  Once every lane
+// has its window in registers the slice is dead and serves as staging area for F and the objective row.
+// tile: the warp's NPP record slots, constants already in place (record_init).
+// needG carries two experiment switches in bits 2 and 3 (tools/kbench.py): 4 = stage but do not store
+// G, 8 = no trigonometry.
 template <int FORM, int WIND>
-__device__ __forceinline__ void tile_eval(const FgConst &c, const double *__restrict__ sx,
-                                          double *__restrict__ tile, const double dt, const int k0,
-                                          const int nk, const int lane, double *__restrict__ Fb,
-                                          double *__restrict__ Gb, const int needF, const int needG,
-                                          const CUtensorMap *gmap, const int bidx, double &sumT,
-                                          double &sump) {
+__device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *tile, const double dt,
+                                          const int k0, const int nk, const int lane,
+                                          double *__restrict__ Fb, double *__restrict__ Gb,
+                                          const int needF, const int needG, double &sumT, double &sump) {
     constexpr bool W = (WIND == 1);
     constexpr bool S10 = (FORM == TOLCUDA_FORM_S10);
     const int ts = c.ts;
     const int k = k0 + lane;
     const bool active = lane < nk;
+    const bool last_window = active && (k == ts - 1);  // also carries node ts
     const double *s0 = sx + 1 + PX * (active ? lane : 0);
     const double *s1 = s0 + PX;
     const double z = s0[2], Va = s0[3], gam = s0[4], chi = s0[5], phi = s0[6], CL = s0[7];
     const double dphi = s0[8], dCL = s0[9], T = s0[10];
 
-    // ---- shared sub-expressions of the window (see window formulas in the file header) ----
+    // ---- shared sub-expressions of the window ----
     double sc, cc, sg, cg, sp, cp;
-    if (needG & 8) {  // experiment switch: no trigonometry
+    if (needG & 8) {
         sc = sg = sp = 0.6, cc = cg = cp = 0.8;
     } else {
         sincos(chi, &sc, &cc);
@@ -138,258 +212,195 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, const double *__rest
         ez = -((Wxz * cg) * sc);  // (dWy_dz*cc*cg - dWx_dz*cg*sc)
         fz = -(Wxzsc * sg);       // (dWy_dz*cc*sg - dWx_dz*sc*sg)
     }
-    // Shared-reciprocal division: x/D is evaluated as div_r(x, D, RN(1/D)) = one product plus one
-    // Markstein correction, which returns the correctly rounded quotient (the same value as IEEE
-    // division) for normal-range operands; the six denominators below serve 26 of a window's divisions.
-    const double rVa = 1.0 / Va;
+    const double rVa = 1.0 / Va, rVacg = 1.0 / Vacg;
     const double CdT = c.Cd0 + div_r(CL * CL, c.ARpiee, c.r_ARpiee);  // (Cd0 + CL*CL/(AR*pi*ee))
-    const double rSV = c.rhoSS * Va;                  // rho*SS*Va
-    const double CLrS = CL * c.rho * c.SS;            // CL*rho*SS
+    const double rSV = c.rhoSS * Va;                                  // rho*SS*Va
+    const double CLrS = CL * c.rho * c.SS;                            // CL*rho*SS
     const double CLrSV = CLrS * Va;
     const double Va2 = Va * Va;
     const double Tmm = div_r(T, c.mm, c.r_mm);
     const double gsg = c.g * sg, gcg = c.g * cg;
     const double n4 = W ? vz * bz - gcg : -gcg;  // (vx*bx + vy*by + vz*bz - g*cos(gam))
     const double Vadt = Va * dt, mdt = -dt;
-    const double rVacg = 1.0 / Vacg;
 
     // ---- objective terms: src/problemS10.cpp:246-258, 340-372; src/problemG7.cpp:240-241, 370 ----
     sumT = 0.0, sump = 0.0;
-    {
-        const bool last_window = active && (k == ts - 1);  // also carries node ts
-        double r0x = 0.0, r0y = 0.0, rex = 0.0, rey = 0.0;
-        const double Te = s1[10];
-        if (active) sumT = T * T;
-        if (last_window) sumT += Te * Te;
-        if (S10) {
-            if (active) {
-                const double ddx = s0[0] - c.xg, ddy = s0[1] - c.yg;
-                const double r = sqrt(ddx * ddx + ddy * ddy);
-                const double rmR = r - c.rg;
-                const double rr = 1.0 / r;
-                sump = rmR * rmR;
-                r0x = div_r(c.kp * rmR * ddx, r, rr);
-                r0y = div_r(c.kp * rmR * ddy, r, rr);
-            }
-            if (last_window) {
-                const double ddx = s1[0] - c.xg, ddy = s1[1] - c.yg;
-                const double r = sqrt(ddx * ddx + ddy * ddy);
-                const double rmR = r - c.rg;
-                const double rr = 1.0 / r;
-                sump += rmR * rmR;
-                rex = div_r(c.kp * rmR * ddx, r, rr);
-                rey = div_r(c.kp * rmR * ddy, r, rr);
-            }
-            if (needG) {
-                // objective row [dt, (x, y, T) of every node]: this warp's 3*nk (+3) entries
-                if (active) {
-                    tile[3 * lane] = r0x;
-                    tile[3 * lane + 1] = r0y;
-                    tile[3 * lane + 2] = c.kT * T;
-                }
-                if (last_window) {
-                    tile[3 * lane + 3] = rex;
-                    tile[3 * lane + 4] = rey;
-                    tile[3 * lane + 5] = c.kT * Te;
-                }
-                __syncwarp();
-                const int cnt0 = 3 * nk + ((k0 + nk == ts) ? 3 : 0);
-                double *dst = Gb + 1 + 3 * k0;
-                for (int i = lane; i < cnt0; i += 32) dst[i] = tile[i];
-                __syncwarp();
-            }
-        } else if (needG) {
-            // G7 objective row [dt, x_0, y_0, T_0 .. T_{ts-1}, x_ts, y_ts, T_ts], src/problemG7.cpp:343-380
-            if (active) Gb[3 + k] = c.kT * T;
-            if (last_window) Gb[ts + 5] = c.kT * Te;
+    double r0x = 0.0, r0y = 0.0, rex = 0.0, rey = 0.0;
+    const double Te = s1[10];
+    if (active) sumT = T * T;
+    if (last_window) sumT += Te * Te;
+    if (S10) {
+        if (active) {
+            const double ddx = s0[0] - c.xg, ddy = s0[1] - c.yg;
+            const double r = sqrt(ddx * ddx + ddy * ddy);
+            const double rmR = r - c.rg;
+            const double rr = 1.0 / r;
+            sump = rmR * rmR;
+            r0x = div_r(c.kp * rmR * ddx, r, rr);
+            r0y = div_r(c.kp * rmR * ddy, r, rr);
+        }
+        if (last_window) {
+            const double ddx = s1[0] - c.xg, ddy = s1[1] - c.yg;
+            const double r = sqrt(ddx * ddx + ddy * ddy);
+            const double rmR = r - c.rg;
+            const double rr = 1.0 / r;
+            sump += rmR * rmR;
+            rex = div_r(c.kp * rmR * ddx, r, rr);
+            rey = div_r(c.kp * rmR * ddy, r, rr);
         }
     }
 
     // ---- defects, src/problem.cpp:1003-1019 ----
+    double f[PF];
+    {
+        const double drag3 = div_r(rSV * Va * CdT, c.twomm, c.r_twomm);
+        const double dx3 = W ? Tmm - vz * az - gsg - drag3 : Tmm - gsg - drag3;
+        const double dx4 = div_r(n4 + div_r(CLrSV * Va * cp, c.twomm, c.r_twomm), Va, rVa);
+        const double lift5 = div_r(CLrSV * Va * sp, c.twomm, c.r_twomm);
+        const double dx5 = W ? div_r(-(vz * cz - lift5), Vacg, rVacg) : div_r(-(-lift5), Vacg, rVacg);
+        f[0] = s1[0] - vx * dt - s0[0];
+        f[1] = s1[1] - vy * dt - s0[1];
+        f[2] = s1[2] - vz * dt - s0[2];
+        f[3] = s1[3] - dx3 * dt - s0[3];
+        f[4] = s1[4] - dx4 * dt - s0[4];
+        f[5] = s1[5] - dx5 * dt - s0[5];
+        f[6] = s1[6] - dphi * dt - s0[6];
+        f[7] = s1[7] - dCL * dt - s0[7];
+    }
+    __syncwarp();  // every lane has read its window: the slice is dead, sx becomes the staging area
+
     if (needF) {
-        {
-            const double drag3 = div_r(rSV * Va * CdT, c.twomm, c.r_twomm);
-            const double dx3 = W ? Tmm - vz * az - gsg - drag3 : Tmm - gsg - drag3;
-            const double dx4 = div_r(n4 + div_r(CLrSV * Va * cp, c.twomm, c.r_twomm), Va, rVa);
-            const double lift5 = div_r(CLrSV * Va * sp, c.twomm, c.r_twomm);
-            const double dx5 = W ? div_r(-(vz * cz - lift5), Vacg, rVacg) : div_r(-(-lift5), Vacg, rVacg);
-            double *f = tile + F_LD * lane;
-            st2(f + 0, s1[0] - vx * dt - s0[0], s1[1] - vy * dt - s0[1]);
-            st2(f + 2, s1[2] - vz * dt - s0[2], s1[3] - dx3 * dt - s0[3]);
-            st2(f + 4, s1[4] - dx4 * dt - s0[4], s1[5] - dx5 * dt - s0[5]);
-            st2(f + 6, s1[6] - dphi * dt - s0[6], s1[7] - dCL * dt - s0[7]);
-        }
+        double *fs = sx + F_LD * lane;
+        st2(fs + 0, f[0], f[1]);
+        st2(fs + 2, f[2], f[3]);
+        st2(fs + 4, f[4], f[5]);
+        st2(fs + 6, f[6], f[7]);
         __syncwarp();
         double *dst = Fb + 1 + PF * k0;
 #pragma unroll
         for (int it = 0; it < PF; it++) {
             const int i = lane + 32 * it;  // i-th defect of the warp: window i/8, state i%8
-            if (i < PF * nk) dst[i] = tile[F_LD * (i >> 3) + (i & 7)];
+            if (i < PF * nk) dst[i] = sx[F_LD * (i >> 3) + (i & 7)];
         }
         __syncwarp();
     }
+    if (!needG) return;
 
-
-    double *q = tile + QREC * lane;  // this lane's quarter record (stride 26 doubles: conflict-free)
-    if (needG) {
-        double *Grec = Gb + c.R0 + (size_t)REC * k0;
-        const bool vec = (reinterpret_cast<uintptr_t>(Grec) & 15) == 0;
-        // Copy-out of one pass.  TMA path (gmap != nullptr): the dense 32 x 26 tile is one box of the 3-D
-        // tensor [B][ts][104] that views the Jacobian records of the whole batch; one lane issues a
-        // cp.async.bulk.tensor store (rows past ts are clipped by the TMA unit) and the warp moves on.
-        // Loop path (outputs not 16-byte aligned): lanes copy 16- or 8-byte words themselves.
-        auto pass_out = [&](double *__restrict__ dst, const int col) {
-            if (needG & 4) {  // experiment switch (tools/kbench.py --need G4): evaluate and stage, store nothing
-                __syncwarp();
-                return;
-            }
-            if (gmap) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) {
-                    asm volatile(
-                        "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
-                        ::"l"(gmap), "r"(col), "r"(k0), "r"(bidx),
-                        "r"((uint32_t)__cvta_generic_to_shared(tile))
-                        : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    // the tile may be rewritten once the TMA unit has read it
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                }
-                __syncwarp();
-                return;
-            }
-            __syncwarp();
-            if (vec) {
-                // 16-byte word i = lane + 32*it of the dense tile belongs to window i/13, position
-                // 2*(i%13) of that window's quarter record
-#pragma unroll
-                for (int it = 0; it < QREC / 2; it++) {
-                    const int i = lane + 32 * it, w = i / (QREC / 2);
-                    if (w < nk)
-                        *reinterpret_cast<double2 *>(dst + w * REC + 2 * (i - w * (QREC / 2))) =
-                            *reinterpret_cast<const double2 *>(tile + 2 * i);
-                }
-            } else {
-                tile_out_scalar<QREC>(dst, REC, tile, nk, lane);
-            }
-            __syncwarp();
-        };
-        // ---- rows F1, F2: src/problem.cpp:1084-1088, 1098-1102 ----
-        {
-            st2(q + 0, -vx, -1.0);
-            st2(q + 2, 0.0, 0.0);
-            st2(q + 4, mdt * cc * cg, Vadt * cc * sg);
-            st2(q + 6, Vadt * cg * sc, 0.0);
-            st2(q + 8, 0.0, 0.0);
-            st2(q + 10, 0.0, 0.0);
-            st2(q + 12, 1.0, -vy);
-            st2(q + 14, 0.0, -1.0);
-            st2(q + 16, 0.0, mdt * cg * sc);
-            st2(q + 18, Vadt * sc * sg, -(Vadt * cc * cg));
-            st2(q + 20, 0.0, 0.0);
-            st2(q + 22, 0.0, 0.0);
-            st2(q + 24, 0.0, 1.0);
+    if (S10) {
+        // objective row [dt, (x, y, T) of every node]: this warp's 3*nk (+3) entries
+        if (active) {
+            sx[3 * lane] = r0x;
+            sx[3 * lane + 1] = r0y;
+            sx[3 * lane + 2] = c.kT * T;
         }
-        pass_out(Grec, 0);
-        // ---- rows F3, F4: :1112-1115, :1125-1130 ----
-        {
-            const double dragv = div_r(rSV * CdT, c.mm, c.r_mm);
-            const double drag11 = div_r(c.rhoSS * Va2 * CdT, c.twomm, c.r_twomm);
-            const double g4dt = W ? vz * az - Tmm + gsg + drag11 : -Tmm + gsg + drag11;
-            const double g4Va = W ? dt * (-(sg * az) + dragv) - 1.0 : dt * dragv - 1.0;
-            const double g4gam = W ? mdt * (n4 + Vacg * az) : mdt * n4;
-            const double g4chi = W ? dt * (ez * vz) : 0.0;
-            const double g4CL = div_r(CLrS * Va2 * dt, c.ARpieemm, c.r_ARpieemm);
-            const double g4T = div_r(mdt, c.mm, c.r_mm);
-            st2(q + 0, Vasg, 0.0);
-            st2(q + 2, 0.0, -1.0);
-            st2(q + 4, dt * sg, Vadt * cg);
-            st2(q + 6, 0.0, 0.0);
-            st2(q + 8, 0.0, 0.0);
-            st2(q + 10, 0.0, 0.0);
-            st2(q + 12, 1.0, g4dt);
-            st2(q + 14, 0.0, 0.0);
-            st2(q + 16, 0.0, g4Va);
-            st2(q + 18, g4gam, g4chi);
-            st2(q + 20, 0.0, g4CL);
-            st2(q + 22, 0.0, 0.0);
-            st2(q + 24, g4T, 1.0);
+        if (last_window) {
+            sx[3 * lane + 3] = rex;
+            sx[3 * lane + 4] = rey;
+            sx[3 * lane + 5] = c.kT * Te;
         }
-        pass_out(Grec + QREC, QREC);
-        // ---- rows F5, F6: :1140-1145, :1155-1160 ----
-        {
-            const double rVa2 = 1.0 / Va2;
-            const double S5 = n4 + div_r(CLrS * Va2 * cp, c.twomm, c.r_twomm);
-            const double liftv = div_r(CLrSV * cp, c.mm, c.r_mm);
-            const double g5dt = div_r(-S5, Va, rVa);
-            const double g5Va = W ? div_r(dt * S5, Va2, rVa2) - div_r(dt * (-(sg * bz) + liftv), Va, rVa)
-                                  : div_r(dt * S5, Va2, rVa2) - div_r(dt * liftv, Va, rVa);
-            const double g5gam = W ? div_r(-(dt * (vz * az + gsg - Vacg * bz)), Va, rVa) - 1.0
-                                   : div_r(-(dt * gsg), Va, rVa) - 1.0;
-            const double g5chi = W ? div_r(-(dt * (fz * vz)), Va, rVa) : 0.0;
-            const double g5phi = div_r(CLrSV * dt * sp, c.twomm, c.r_twomm);
-            const double g5CL = div_r(-(rSV * dt * cp), c.twomm, c.r_twomm);
-            const double lift6 = div_r(CLrS * Va2 * sp, c.twomm, c.r_twomm);
-            const double Q = W ? vz * cz - lift6 : -lift6;
-            const double sidev = div_r(CLrSV * sp, c.mm, c.r_mm);
-            const double Va2cg = Va2 * cg, Vacg2 = Va * (cg * cg), tmcg = c.twomm * cg;
-            const double rVa2cg = 1.0 / Va2cg, rVacg2 = 1.0 / Vacg2, rtmcg = 1.0 / tmcg;
-            const double g6dt = div_r(Q, Vacg, rVacg);
-            const double g6Va = W ? div_r(-(dt * (sg * cz + sidev)), Vacg, rVacg) - div_r(dt * Q, Va2cg, rVa2cg)
-                                  : div_r(-(dt * sidev), Vacg, rVacg) - div_r(dt * Q, Va2cg, rVa2cg);
-            const double g6gam = W ? div_r(dt * sg * Q, Vacg2, rVacg2) - div_r(dt * (Vacg * cz), Vacg, rVacg)
-                                   : div_r(dt * sg * Q, Vacg2, rVacg2);
-            const double g6chi = W ? div_r(-(dt * (vz * dz)), Vacg, rVacg) - 1.0 : -1.0;
-            const double g6phi = div_r(-(CLrSV * dt * cp), tmcg, rtmcg);
-            const double g6CL = div_r(-(rSV * dt * sp), tmcg, rtmcg);
-            st2(q + 0, g5dt, 0.0);
-            st2(q + 2, 0.0, 0.0);
-            st2(q + 4, g5Va, g5gam);
-            st2(q + 6, g5chi, g5phi);
-            st2(q + 8, g5CL, 0.0);
-            st2(q + 10, 0.0, 0.0);
-            st2(q + 12, 1.0, g6dt);
-            st2(q + 14, 0.0, 0.0);
-            st2(q + 16, 0.0, g6Va);
-            st2(q + 18, g6gam, g6chi);
-            st2(q + 20, g6phi, g6CL);
-            st2(q + 22, 0.0, 0.0);
-            st2(q + 24, 0.0, 1.0);
-        }
-        pass_out(Grec + 2 * QREC, 2 * QREC);
-        // ---- rows F7, F8: :1170-1172, :1182-1184 ----
-        {
-            st2(q + 0, -dphi, 0.0);
-            st2(q + 2, 0.0, 0.0);
-            st2(q + 4, 0.0, 0.0);
-            st2(q + 6, 0.0, -1.0);
-            st2(q + 8, 0.0, mdt);
-            st2(q + 10, 0.0, 0.0);
-            st2(q + 12, 1.0, -dCL);
-            st2(q + 14, 0.0, 0.0);
-            st2(q + 16, 0.0, 0.0);
-            st2(q + 18, 0.0, 0.0);
-            st2(q + 20, 0.0, -1.0);
-            st2(q + 22, 0.0, mdt);
-            st2(q + 24, 0.0, 1.0);
-        }
-        pass_out(Grec + 3 * QREC, 3 * QREC);
+        __syncwarp();
+        const int cnt0 = 3 * nk + ((k0 + nk == ts) ? 3 : 0);
+        double *dst = Gb + 1 + 3 * k0;
+        for (int i = lane; i < cnt0; i += 32) dst[i] = sx[i];
+    } else {
+        // G7 objective row [dt, x_0, y_0, T_0 .. T_{ts-1}, x_ts, y_ts, T_ts], src/problemG7.cpp:343-380
+        if (active) Gb[3 + k] = c.kT * T;
+        if (last_window) Gb[ts + 5] = c.kT * Te;
     }
 
+    // ---- Jacobian rows, src/problem.cpp:1074-1192 ----
+    double v[NVAR];
+    v[0] = -vx;  // F1 :1084-1088
+    v[1] = mdt * cc * cg;
+    v[2] = Vadt * cc * sg;
+    v[3] = Vadt * cg * sc;
+    v[4] = -vy;  // F2 :1098-1102
+    v[5] = mdt * cg * sc;
+    v[6] = Vadt * sc * sg;
+    v[7] = -(Vadt * cc * cg);
+    v[8] = Vasg;  // F3 :1112-1115
+    v[9] = dt * sg;
+    v[10] = Vadt * cg;
+    {  // F4 :1125-1130
+        const double dragv = div_r(rSV * CdT, c.mm, c.r_mm);
+        const double drag11 = div_r(c.rhoSS * Va2 * CdT, c.twomm, c.r_twomm);
+        v[11] = W ? vz * az - Tmm + gsg + drag11 : -Tmm + gsg + drag11;
+        v[12] = W ? dt * (-(sg * az) + dragv) - 1.0 : dt * dragv - 1.0;
+        v[13] = W ? mdt * (n4 + Vacg * az) : mdt * n4;
+        v[14] = W ? dt * (ez * vz) : 0.0;
+        v[15] = div_r(CLrS * Va2 * dt, c.ARpieemm, c.r_ARpieemm);
+        v[16] = div_r(mdt, c.mm, c.r_mm);
+    }
+    {  // F5 :1140-1145
+        const double rVa2 = 1.0 / Va2;
+        const double S5 = n4 + div_r(CLrS * Va2 * cp, c.twomm, c.r_twomm);
+        const double liftv = div_r(CLrSV * cp, c.mm, c.r_mm);
+        v[17] = div_r(-S5, Va, rVa);
+        v[18] = W ? div_r(dt * S5, Va2, rVa2) - div_r(dt * (-(sg * bz) + liftv), Va, rVa)
+                  : div_r(dt * S5, Va2, rVa2) - div_r(dt * liftv, Va, rVa);
+        v[19] = W ? div_r(-(dt * (vz * az + gsg - Vacg * bz)), Va, rVa) - 1.0 : div_r(-(dt * gsg), Va, rVa) - 1.0;
+        v[20] = W ? div_r(-(dt * (fz * vz)), Va, rVa) : 0.0;
+        v[21] = div_r(CLrSV * dt * sp, c.twomm, c.r_twomm);
+        v[22] = div_r(-(rSV * dt * cp), c.twomm, c.r_twomm);
+    }
+    {  // F6 :1155-1160
+        const double lift6 = div_r(CLrS * Va2 * sp, c.twomm, c.r_twomm);
+        const double Q = W ? vz * cz - lift6 : -lift6;
+        const double sidev = div_r(CLrSV * sp, c.mm, c.r_mm);
+        const double Va2cg = Va2 * cg, Vacg2 = Va * (cg * cg), tmcg = c.twomm * cg;
+        const double rVa2cg = 1.0 / Va2cg, rVacg2 = 1.0 / Vacg2, rtmcg = 1.0 / tmcg;
+        v[23] = div_r(Q, Vacg, rVacg);
+        v[24] = W ? div_r(-(dt * (sg * cz + sidev)), Vacg, rVacg) - div_r(dt * Q, Va2cg, rVa2cg)
+                  : div_r(-(dt * sidev), Vacg, rVacg) - div_r(dt * Q, Va2cg, rVa2cg);
+        v[25] = W ? div_r(dt * sg * Q, Vacg2, rVacg2) - div_r(dt * (Vacg * cz), Vacg, rVacg)
+                  : div_r(dt * sg * Q, Vacg2, rVacg2);
+        v[26] = W ? div_r(-(dt * (vz * dz)), Vacg, rVacg) - 1.0 : -1.0;
+        v[27] = div_r(-(CLrSV * dt * cp), tmcg, rtmcg);
+        v[28] = div_r(-(rSV * dt * sp), tmcg, rtmcg);
+    }
+    v[29] = -dphi;  // F7 :1172
+    v[30] = -dCL;   // F8 :1184
+
+    // ---- drain: groups of NPP windows through the record slots, whole records to global ----
+    double *Grec = Gb + c.R0 + (size_t)REC * k0;  // record of window k0
+    const bool bulk = (reinterpret_cast<uintptr_t>(Grec) & 15) == 0;
+    double *slot = tile + (lane & (NPP - 1)) * REC_LD;
+#pragma unroll 1
+    for (int g = 0; g < 32 / NPP; g++) {
+        if (g * NPP >= nk) break;
+        const bool mine = (lane / NPP) == g;
+        if (mine) record_store(slot, v, mdt);
+        if (needG & 4) {
+            __syncwarp();
+        } else if (bulk) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (mine && active) {
+                bulk_store_record(Grec + (size_t)REC * lane, slot);
+                bulk_wait_read();  // the slot may be rewritten once the TMA unit has read it
+            }
+            __syncwarp();
+        } else {
+            __syncwarp();
+            const int cnt = min(NPP, nk - g * NPP) * REC;
+            double *dst = Grec + (size_t)REC * NPP * g;
+            for (int i = lane; i < cnt; i += 32) {
+                const int r = i / REC;
+                dst[i] = tile[r * REC_LD + (i - r * REC)];
+            }
+            __syncwarp();
+        }
+    }
 }
 
 // Out-of-line instance for the persistent kernel: inlined into its trajectory/tile loop, ptxas keeps
-// ~60 extra doubles live across the loop and spills ~500 bytes per thread at the 128-register budget;
-// as a call the tile body is allocated on its own and does not spill.
+// dozens of extra values live across the loop and spills; as a call the tile body is allocated on its own.
 template <int FORM, int WIND>
-__device__ __noinline__ void tile_eval_call(const FgConst &c, const double *sx, double *tile,
-                                            const double dt, const int k0,
-                                            const int nk, const int lane, double *__restrict__ Fb,
-                                            double *__restrict__ Gb, const int needF, const int needG,
-                                            const CUtensorMap *gmap, const int bidx, double &sumT,
-                                            double &sump) {
-    tile_eval<FORM, WIND>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, gmap, bidx, sumT, sump);
+__device__ __noinline__ void tile_eval_call(const FgConst &c, double *sx, double *tile, const double dt,
+                                            const int k0, const int nk, const int lane,
+                                            double *__restrict__ Fb, double *__restrict__ Gb,
+                                            const int needF, const int needG, double &sumT, double &sump) {
+    tile_eval<FORM, WIND>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, sumT, sump);
 }
 
 // ---- end of a trajectory: F[0], boundary rows, objective-row ends --------------------------------------
@@ -467,58 +478,26 @@ __device__ __forceinline__ void traj_epilogue(const FgConst &c, const int lane, 
     }
 }
 
-// ---- asynchronous global -> shared copies (LDGSTS) -------------------------------------------------------
-__device__ __forceinline__ void cp_async16(double *dst, const double *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
-}
-__device__ __forceinline__ void cp_async8(double *dst, const double *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-// enqueue the copy of `cnt` doubles xs[0..cnt) into sx[0..cnt): 16-byte pieces when xs allows it
-__device__ __forceinline__ void slice_prefetch(double *sx, const double *xs, const int cnt, const int lane) {
-    if ((reinterpret_cast<uintptr_t>(xs) & 15) == 0) {
-#pragma unroll
-        for (int it = 0; it < (SX_LEN / 2 + 31) / 32; it++) {
-            const int i = lane + 32 * it;
-            if (2 * i + 1 < cnt) cp_async16(sx + 2 * i, xs + 2 * i);
-            else if (2 * i < cnt) cp_async8(sx + 2 * i, xs + 2 * i);
-        }
-    } else {
-        for (int i = lane; i < cnt; i += 32) cp_async8(sx + i, xs + i);
-    }
-}
-
 // ---- kernel A: one CTA per trajectory ------------------------------------------------------------------
 //
 // grid.x = B, blockDim.x = 32*ceil(ts/32) (<= MAXT).  Warp w owns windows 32w..32w+31 and runs on its
 // own after start-up; the cost sum crosses warps through shared memory and an arrival counter, and the
-// last warp to arrive runs the trajectory epilogue.  Best when B is small (down to the single
-// trajectory of the snOptA callback): all tiles of a trajectory proceed in parallel.
+// last warp to arrive runs the trajectory epilogue.
 template <int FORM, int WIND, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
-fg_cta_kernel(const __grid_constant__ FgConst c, const __grid_constant__ CUtensorMap gmap, int use_tma,
-              const double *__restrict__ x, long ldx, double *__restrict__ F, long ldF,
-              double *__restrict__ G, long ldG, int needF, int needG) {
-    extern __shared__ __align__(128) double smem[];
+fg_cta_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, long ldx,
+              double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG) {
+    extern __shared__ __align__(16) double smem[];
     __shared__ double red[2][32];
     __shared__ int arrivals;
     const int ts = c.ts;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    double *sx = smem + (size_t)warp * WARP_SMEM_A;
+    double *sx = smem + (size_t)warp * WARP_SMEM;
     double *tile = sx + SX_LEN;
     const size_t b = blockIdx.x;
     const double *xb = x + b * ldx;
     double *Fb = F + b * ldF;
     double *Gb = G + b * ldG;
-
-    if (threadIdx.x == 0) arrivals = 0;
-    __syncthreads();
 
     // stage this warp's x slice: doubles [11*k0, 11*k0 + 1 + 11*(nk+1)) of the trajectory
     const int k0 = 32 * warp;
@@ -526,12 +505,14 @@ fg_cta_kernel(const __grid_constant__ FgConst c, const __grid_constant__ CUtenso
     slice_prefetch(sx, xb + (size_t)PX * k0, 1 + PX * (nk + 1), lane);
     cp_async_commit();
     const double dt = __ldg(xb);
+    if (needG && lane < NPP) record_init(tile + lane * REC_LD);
+    if (threadIdx.x == 0) arrivals = 0;
+    __syncthreads();
     cp_async_wait<0>();
     __syncwarp();
 
     double sumT, sump;
-    tile_eval<FORM, WIND>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, use_tma ? &gmap : nullptr,
-                          (int)b, sumT, sump);
+    tile_eval<FORM, WIND>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, sumT, sump);
 
     // cost sums: warp shuffle, then across warps through shared memory
     sumT = warp_sum(sumT);
@@ -565,41 +546,37 @@ fg_cta_kernel(const __grid_constant__ FgConst c, const __grid_constant__ CUtenso
 // Every warp walks trajectories b = warp_id, warp_id + total_warps, ... and, within a trajectory, its
 // tiles in order, so cost sums stay in registers and no warp ever waits for another.  While a tile is
 // evaluated, the x slice of the next tile (or of the next trajectory's first tile) is already in flight
-// (cp.async) into the other slice buffer, which hides the read latency behind the write stream.
-// The tile body is called out of line (tile_eval_call): inlined into this loop it costs ~500 bytes of
-// spills per thread.  Measured slower than kernel A on B200 at every batch size tried so far; kept as a
-// selectable variant (TOLCUDA_KERNEL=2).
+// (cp.async) into the other slice buffer.  Selectable variant (TOLCUDA_KERNEL=2).
 template <int FORM, int WIND, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
-fg_warp_kernel(const __grid_constant__ FgConst c, const __grid_constant__ CUtensorMap gmap, int use_tma,
-               int B, const double *__restrict__ x, long ldx, double *__restrict__ F, long ldF,
-               double *__restrict__ G, long ldG, int needF, int needG) {
-    extern __shared__ __align__(128) double smem[];
+fg_warp_kernel(const __grid_constant__ FgConst c, int B, const double *__restrict__ x, long ldx,
+               double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG) {
+    extern __shared__ __align__(16) double smem[];
     const int ts = c.ts;
     const int nt = (ts + 31) >> 5;
-    const int lane0 = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *wsm = smem + (size_t)warp * WARP_SMEM_B;
+    double *tile = wsm + 2 * SX_LEN;
     const int total = gridDim.x * WARPS;
     int b = blockIdx.x * WARPS + warp, t = 0, buf = 0;
     if (b >= B) return;
 
-    slice_prefetch(wsm, x + (size_t)b * ldx, 1 + PX * (min(32, ts) + 1), lane0);
+    slice_prefetch(wsm, x + (size_t)b * ldx, 1 + PX * (min(32, ts) + 1), lane);
     cp_async_commit();
+    if (needG && lane < NPP) record_init(tile + lane * REC_LD);
     double dt = 0.0, n0 = 0.0, accT = 0.0, accp = 0.0;
 #pragma unroll 1
     while (b < B) {
-        const int lane = lane0;
         int nb = b, ntile = t + 1;
         if (ntile == nt) {
             nb = b + total;
             ntile = 0;
         }
-        double *sx = wsm + buf * SX_LEN;             // current slice
-        double *sx_next = wsm + (buf ^ 1) * SX_LEN;  // the other slice
-        double *tile = wsm + 2 * SX_LEN;
+        double *sx = wsm + buf * SX_LEN;  // current slice; the other one receives the prefetch
         if (nb < B) {
             const int nk2 = min(32, ts - 32 * ntile);
-            slice_prefetch(sx_next, x + (size_t)nb * ldx + (size_t)PX * 32 * ntile, 1 + PX * (nk2 + 1), lane);
+            slice_prefetch(wsm + (buf ^ 1) * SX_LEN, x + (size_t)nb * ldx + (size_t)PX * 32 * ntile,
+                           1 + PX * (nk2 + 1), lane);
         }
         cp_async_commit();
         cp_async_wait<1>();
@@ -613,8 +590,7 @@ fg_warp_kernel(const __grid_constant__ FgConst c, const __grid_constant__ CUtens
         const double ne = (t == nt - 1 && lane < PX) ? sx[1 + PX * nk + lane] : 0.0;
         double *Fb = F + (size_t)b * ldF, *Gb = G + (size_t)b * ldG;
         double sumT, sump;
-        tile_eval_call<FORM, WIND>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, use_tma ? &gmap : nullptr,
-                                   b, sumT, sump);
+        tile_eval_call<FORM, WIND>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, sumT, sump);
         accT += sumT;
         accp += sump;
         if (t == nt - 1) {
@@ -623,7 +599,7 @@ fg_warp_kernel(const __grid_constant__ FgConst c, const __grid_constant__ CUtens
             traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG);
             accT = accp = 0.0;
         }
-        __syncwarp();  // every lane is done with the tile before the next iteration's prefetch reuses it
+        __syncwarp();
         b = nb;
         t = ntile;
         buf ^= 1;
@@ -635,14 +611,14 @@ template <int FORM, int WIND, int MAXT, int MINB>
 cudaError_t launch_cta(const FgLaunch &L) {
     auto kern = fg_cta_kernel<FORM, WIND, MAXT, MINB>;
     const int nthr = 32 * ((L.c->ts + 31) / 32);
-    const size_t smem = sizeof(double) * (size_t)(nthr / 32) * WARP_SMEM_A;
+    const size_t smem = sizeof(double) * (size_t)(nthr / 32) * WARP_SMEM;
     static size_t configured = 0;  // per instantiation
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    kern<<<L.B, nthr, smem, L.stream>>>(*L.c, L.gmap ? *L.gmap : CUtensorMap(), L.gmap != nullptr, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG);
+    kern<<<L.B, nthr, smem, L.stream>>>(*L.c, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG);
     return cudaGetLastError();
 }
 
@@ -659,22 +635,18 @@ cudaError_t launch_warp(const FgLaunch &L) {
     const int resident = L.sm_count * MINB;  // persistent: one wave of CTAs
     const int want = (L.B + WARPS - 1) / WARPS;
     const int grid = want < resident ? want : resident;
-    kern<<<grid, WARPS * 32, smem, L.stream>>>(*L.c, L.gmap ? *L.gmap : CUtensorMap(), L.gmap != nullptr, L.B, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF,
-                                               L.needG);
+    kern<<<grid, WARPS * 32, smem, L.stream>>>(*L.c, L.B, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG);
     return cudaGetLastError();
 }
 
 template <int FORM, int WIND>
 cudaError_t launch_any(const FgLaunch &L) {
-    // kernel A unless kernel B is asked for (L.kernel == 2; tests, tuning)
-    const bool use_warp = L.kernel == 2;
-    if (use_warp) {
-        return launch_warp<FORM, WIND, 4, 4>(L);  // 128 registers, 16 warps / SM
-    }
-    // register budget per block-size class: 65536 / (MAXT * MINB)
-    if (L.c->ts <= 128) return launch_cta<FORM, WIND, 128, 5>(L);
-    if (L.c->ts <= 256) return launch_cta<FORM, WIND, 256, 3>(L);
-    if (L.c->ts <= 512) return launch_cta<FORM, WIND, 512, 1>(L);
+    if (L.kernel == 2) return launch_warp<FORM, WIND, 4, 4>(L);  // 128 registers, 16 warps / SM
+    // kernel A; register budget per block-size class = 65536 / (MAXT * MINB)
+    const int ts = L.c->ts;
+    if (ts <= 128) return L.kernel == 3 ? launch_cta<FORM, WIND, 128, 5>(L) : launch_cta<FORM, WIND, 128, 4>(L);
+    if (ts <= 256) return L.kernel == 3 ? launch_cta<FORM, WIND, 256, 3>(L) : launch_cta<FORM, WIND, 256, 2>(L);
+    if (ts <= 512) return launch_cta<FORM, WIND, 512, 1>(L);
     return launch_cta<FORM, WIND, 1024, 1>(L);
 }
 

@@ -2,7 +2,6 @@
 #ifndef TOLCUDA_FG_LAUNCH_H_
 #define TOLCUDA_FG_LAUNCH_H_
 
-#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "fg_const.h"
@@ -20,9 +19,8 @@ struct FgLaunch {
     double *G;
     long ldG;
     int needF, needG;
-    const CUtensorMap *gmap;  // 3-D view [B][ts][104] of the Jacobian records of G, or nullptr when G is not
-                              // 16-byte aligned (then lanes copy the tiles out themselves)
-    int kernel;    // 0 = choose by batch size, 1 = kernel A (CTA per trajectory), 2 = kernel B (persistent warps)
+    int kernel;    // 0/1 = kernel A (CTA per trajectory), 2 = kernel B (persistent warps), 3 = kernel A compiled
+                   // for one more resident CTA per SM (fewer registers)
     int sm_count;  // SMs of the device
     cudaStream_t stream;
 };

@@ -1,7 +1,6 @@
 // libtolcuda C ABI (include/tolcuda.h): contexts, constant upload, streams, pinned staging and the
 // host/device batch paths around the sm_100a kernels of fg_kernels.cu.  No CPU evaluation path
 // exists in this library: if CUDA is unavailable every evaluation call fails with the CUDA error.
-#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -58,12 +57,6 @@ struct tolcuda_ctx {
     // host-pointer batch path
     BatchLane lane[2];
     long launches = 0;
-    // TMA descriptor of the last G buffer seen (re-encoded only when the buffer changes)
-    CUtensorMap gmap;
-    const double *gmap_G = nullptr;
-    long gmap_ldG = 0;
-    int gmap_B = 0;
-    int no_tma = 0;  // TOLCUDA_NO_TMA=1: always use the lane copy-out path (tests)
 };
 
 namespace {
@@ -73,58 +66,9 @@ tolcuda_ctx *g_bound = nullptr;
 
 long round_up(long v, long m) { return (v + m - 1) / m * m; }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_tiled() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-        else
-            cudaGetLastError();
-    }
-    return fn;
-}
-
-// The Jacobian records of a batch, G[b*ldG + R0 + 104*k + j], as a rank-3 FP64 tensor {104, ts, B} whose
-// 26 x 32 x 1 boxes are the quarter-record tiles a warp stores per pass.  Needs 16-byte aligned base and
-// strides; returns nullptr when the buffer does not qualify (the kernels then copy out lane by lane).
-const CUtensorMap *jacobian_map(tolcuda_ctx *h, int B, double *G, long ldG) {
-    if (h->no_tma || !G) return nullptr;
-    const FgConst &c = h->c;
-    double *base = G + c.R0;
-    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ldG & 1) != 0) return nullptr;
-    if (h->gmap_G == G && h->gmap_ldG == ldG && h->gmap_B == B) return &h->gmap;
-    EncodeTiledFn enc = encode_tiled();
-    if (!enc) return nullptr;
-    const cuuint64_t dims[3] = {(cuuint64_t)TOLCUDA_REC, (cuuint64_t)c.ts, (cuuint64_t)B};
-    const cuuint64_t strides[2] = {(cuuint64_t)TOLCUDA_REC * sizeof(double), (cuuint64_t)ldG * sizeof(double)};
-    const cuuint32_t box[3] = {26, 32, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&h->gmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        h->gmap_G = nullptr;
-        return nullptr;
-    }
-    h->gmap_G = G, h->gmap_ldG = ldG, h->gmap_B = B;
-    return &h->gmap;
-}
-
 int launch(tolcuda_ctx *h, cudaStream_t st, int B, const double *x, long ldx, double *F, long ldF,
            double *G, long ldG, int needF, int needG) {
     FgLaunch L;
-    L.gmap = needG ? jacobian_map(h, B, G, ldG) : nullptr;
     L.c = &h->c;
     L.B = B;
     L.x = x, L.ldx = ldx, L.F = F, L.ldF = ldF, L.G = G, L.ldG = ldG;
@@ -240,7 +184,6 @@ int tolcuda_create(const tolcuda_config *cfg, tolcuda_handle *out) {
     pattern_build(c.form, c.ts, h->iG, h->jG);
 
     if (const char *env = std::getenv("TOLCUDA_KERNEL")) h->kernel = std::atoi(env);  // tests / tuning
-    if (const char *env = std::getenv("TOLCUDA_NO_TMA")) h->no_tma = std::atoi(env);
 
     int rc = 0;
     do {
