@@ -166,7 +166,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except OSError:
@@ -219,6 +219,11 @@ def ncu_traffic(wl_name):
         except ValueError:
             return None
     return None
+
+
+def scaled_traffic(wl_name, alg_bytes):
+    t = ncu_traffic(wl_name)
+    return None if not t else t["ratio"] * alg_bytes
 
 
 def run_ours(args, wl_name):
@@ -343,8 +348,8 @@ def run_ours(args, wl_name):
                 "api": "tolcuda_eval_batch(TOLCUDA_HOST_PTRS), pinned host x/F/G"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(wl_name), "peak_source": peak_src,
-                     "kernel": "fg_batch_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+                     "traffic": scaled_traffic(wl_name, alg_bytes), "traffic_source": "profiles/roofline_traffic.json (ncu --set full at B=8192, ratio to algorithmic bytes applied)", "peak_source": peak_src,
+                     "kernel": "fg_cta_kernel<S10, wind 1, 256, 2>", "algorithmic_bytes_per_launch": alg_bytes,
                      "launch_ms": launch_ms},
         "clocks": clocks,
     }

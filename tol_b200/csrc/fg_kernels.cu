@@ -30,10 +30,10 @@
 // (208-byte pieces measured 4.8 TB/s against 7.5 TB/s for a plain fill).  So G leaves as whole
 // 832-byte window records, contiguous in SNOPT coordinate order:
 //   * each warp stages the 33-node slice of x its windows need in shared memory (cp.async, 16-byte);
-//   * a window's 104-value record is assembled in a per-warp tile of 8 record slots whose structural
-//     constants (0, +-1) are written once; per group of 8 windows only the 33 x-dependent entries are
-//     stored (lane stride 106 doubles: conflict-free), and each lane then hands its finished record to
-//     the TMA unit as one cp.async.bulk shared->global copy;
+//   * a window's 104-value record is assembled in one of the warp's 2 x 4 record slots whose structural
+//     constants (0, +-1) are written once; per group of 4 windows only the 33 x-dependent entries are
+//     stored, and the 4 finished records (3,328 contiguous bytes) go to the TMA unit as one
+//     cp.async.bulk shared->global copy while the lanes fill the other buffer;
 //   * F (8 defects per window) and the S10 objective-row entries go out through the dead x slice as
 //     coalesced stores.  Cost sums use warp-shuffle reductions.
 #include <cuda_runtime.h>
@@ -48,11 +48,10 @@ namespace {
 constexpr int PX = TOLCUDA_PX;
 constexpr int PF = TOLCUDA_PF;
 constexpr int REC = TOLCUDA_REC;
-constexpr int REC_LD = 106;            // smem stride of a record slot: 16-byte aligned and == 2 (mod 4), so
-                                       // 8-/16-byte stores of consecutive lanes fall in distinct banks
-constexpr int NPP = 8;                 // record slots per warp tile = windows drained per group
+constexpr int NPP = 4;                 // windows drained per group: one dense buffer of NPP records
+constexpr int NBUF = 2;                // record buffers per warp (the TMA unit reads one while lanes fill the other)
 constexpr int SX_LEN = 368;            // a warp's x slice: slot for x[11*k0] + 33 nodes = 364 doubles
-constexpr int TILE_LEN = NPP * REC_LD; // 848 doubles
+constexpr int TILE_LEN = NBUF * NPP * REC;  // 832 doubles
 constexpr int WARP_SMEM = SX_LEN + TILE_LEN;        // kernel A
 constexpr int WARP_SMEM_B = 2 * SX_LEN + TILE_LEN;  // kernel B: double-buffered x slice
 constexpr int F_LD = 10;               // smem stride of a window's 8 defects (== 2 mod 4)
@@ -101,14 +100,19 @@ __device__ __forceinline__ void slice_prefetch(double *sx, const double *xs, con
     }
 }
 
-// TMA bulk copy shared -> global of one record (832 bytes, both sides 16-byte aligned)
-__device__ __forceinline__ void bulk_store_record(double *gdst, const double *ssrc) {
+// TMA bulk copy shared -> global of `bytes` (a multiple of 16; both sides 16-byte aligned), as its own
+// bulk group of the calling thread
+__device__ __forceinline__ void bulk_store(double *gdst, const double *ssrc, const int bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-                 "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "n"(REC * 8)
+                 "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// wait until all but the newest N bulk groups of the calling thread have finished READING shared memory
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 
 // ---- record slots -------------------------------------------------------------------------------------
 //
@@ -160,7 +164,7 @@ __device__ __forceinline__ void record_store(double *rec, const double *v, const
 //
 // sx: the warp's staged x slice (slot 0 = x[11*k0], node j of the slice at sx[1+11j]).  Once every lane
 // has its window in registers the slice is dead and serves as staging area for F and the objective row.
-// tile: the warp's NPP record slots, constants already in place (record_init).
+// tile: the warp's NBUF x NPP record slots, constants already in place (record_init).
 // needG carries two experiment switches in bits 2 and 3 (tools/kbench.py): 4 = stage but do not store
 // G, 8 = no trigonometry.
 template <int FORM, int WIND>
@@ -361,35 +365,39 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
     v[29] = -dphi;  // F7 :1172
     v[30] = -dCL;   // F8 :1184
 
-    // ---- drain: groups of NPP windows through the record slots, whole records to global ----
+    // ---- drain: groups of NPP windows through the two record buffers, whole records to global ----
+    // Group g (windows k0+NPP*g ..) fills buffer g&1 while the TMA unit may still be reading the other
+    // one; lane 0 issues every bulk copy (NPP contiguous records = NPP*832 bytes) and owns the bulk
+    // groups.  The buffers are dense, as the copy needs: the NPP lanes of a group store at a stride of
+    // 832 bytes, a 2-way bank conflict.
     double *Grec = Gb + c.R0 + (size_t)REC * k0;  // record of window k0
     const bool bulk = (reinterpret_cast<uintptr_t>(Grec) & 15) == 0;
-    double *slot = tile + (lane & (NPP - 1)) * REC_LD;
 #pragma unroll 1
     for (int g = 0; g < 32 / NPP; g++) {
         if (g * NPP >= nk) break;
-        const bool mine = (lane / NPP) == g;
-        if (mine) record_store(slot, v, mdt);
+        double *buf = tile + (g & 1) * (NPP * REC);
+        if (bulk && g >= NBUF) {
+            if (lane == 0) bulk_wait_read<NBUF - 1>();  // group g-2 has been read: its buffer is free
+            __syncwarp();
+        }
+        if ((lane / NPP) == g) record_store(buf + (lane & (NPP - 1)) * REC, v, mdt);
+        const int cnt = min(NPP, nk - g * NPP) * REC;
+        double *dst = Grec + (size_t)REC * NPP * g;
         if (needG & 4) {
             __syncwarp();
         } else if (bulk) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (mine && active) {
-                bulk_store_record(Grec + (size_t)REC * lane, slot);
-                bulk_wait_read();  // the slot may be rewritten once the TMA unit has read it
-            }
-            __syncwarp();
+            if (lane == 0) bulk_store(dst, buf, cnt * 8);
         } else {
             __syncwarp();
-            const int cnt = min(NPP, nk - g * NPP) * REC;
-            double *dst = Grec + (size_t)REC * NPP * g;
-            for (int i = lane; i < cnt; i += 32) {
-                const int r = i / REC;
-                dst[i] = tile[r * REC_LD + (i - r * REC)];
-            }
+            for (int i = lane; i < cnt; i += 32) dst[i] = buf[i];
             __syncwarp();
         }
+    }
+    if (bulk) {
+        if (lane == 0) bulk_wait_read<0>();  // the buffers are reused (or released) after this
+        __syncwarp();
     }
 }
 
@@ -505,7 +513,12 @@ fg_cta_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, l
     slice_prefetch(sx, xb + (size_t)PX * k0, 1 + PX * (nk + 1), lane);
     cp_async_commit();
     const double dt = __ldg(xb);
-    if (needG && lane < NPP) record_init(tile + lane * REC_LD);
+    double n0 = 0.0, ne = 0.0;  // node 0 / node ts, for whichever warp ends up running the epilogue
+    if (lane < PX) {
+        n0 = __ldg(xb + 1 + lane);
+        ne = __ldg(xb + (size_t)PX * ts + 1 + lane);
+    }
+    if (needG && lane < NBUF * NPP) record_init(tile + lane * REC);
     if (threadIdx.x == 0) arrivals = 0;
     __syncthreads();
     cp_async_wait<0>();
@@ -533,11 +546,6 @@ fg_cta_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, l
         tT += vred[w];
         tp += vred[32 + w];
     }
-    double n0 = 0.0, ne = 0.0;
-    if (lane < PX) {
-        n0 = __ldg(xb + 1 + lane);
-        ne = __ldg(xb + (size_t)PX * ts + 1 + lane);
-    }
     traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG);
 }
 
@@ -563,7 +571,7 @@ fg_warp_kernel(const __grid_constant__ FgConst c, int B, const double *__restric
 
     slice_prefetch(wsm, x + (size_t)b * ldx, 1 + PX * (min(32, ts) + 1), lane);
     cp_async_commit();
-    if (needG && lane < NPP) record_init(tile + lane * REC_LD);
+    if (needG && lane < NBUF * NPP) record_init(tile + lane * REC);
     double dt = 0.0, n0 = 0.0, accT = 0.0, accp = 0.0;
 #pragma unroll 1
     while (b < B) {
@@ -644,8 +652,8 @@ cudaError_t launch_any(const FgLaunch &L) {
     if (L.kernel == 2) return launch_warp<FORM, WIND, 4, 4>(L);  // 128 registers, 16 warps / SM
     // kernel A; register budget per block-size class = 65536 / (MAXT * MINB)
     const int ts = L.c->ts;
-    if (ts <= 128) return L.kernel == 3 ? launch_cta<FORM, WIND, 128, 5>(L) : launch_cta<FORM, WIND, 128, 4>(L);
-    if (ts <= 256) return L.kernel == 3 ? launch_cta<FORM, WIND, 256, 3>(L) : launch_cta<FORM, WIND, 256, 2>(L);
+    if (ts <= 128) return launch_cta<FORM, WIND, 128, 4>(L);
+    if (ts <= 256) return launch_cta<FORM, WIND, 256, 2>(L);
     if (ts <= 512) return launch_cta<FORM, WIND, 512, 1>(L);
     return launch_cta<FORM, WIND, 1024, 1>(L);
 }

@@ -19,8 +19,7 @@ struct FgLaunch {
     double *G;
     long ldG;
     int needF, needG;
-    int kernel;    // 0/1 = kernel A (CTA per trajectory), 2 = kernel B (persistent warps), 3 = kernel A compiled
-                   // for one more resident CTA per SM (fewer registers)
+    int kernel;    // 0/1 = kernel A (CTA per trajectory), 2 = kernel B (persistent warps)
     int sm_count;  // SMs of the device
     cudaStream_t stream;
 };
