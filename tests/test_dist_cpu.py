@@ -1,0 +1,70 @@
+"""CPU, world_size 2, gloo: the host-side logic of the multi-GPU path -- shard ranges by trajectory index,
+per-index input seeding, host-side gather of per-trajectory rows, max-over-ranks timing.  The evaluator
+here is the oracle port (tests may use it); on GPUs the same code wraps tolcuda_eval_batch (bench.py)."""
+import os
+import socket
+
+import numpy as np
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import load_golden, port_from_golden
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, B, out_path):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "oracle"), os.path.join(root, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import tol_b200.dist as D
+    import tol_b200.synth as synth
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = load_golden("S10_skywalker_ts7_gains")
+    p = port_from_golden(g)
+    b0, b1 = D.my_shard(B)
+    X = synth.batch(g["x"][0], 4242, b0, b1)
+    F, G = np.empty((b1 - b0, p.neF)), np.empty((b1 - b0, p.neG))
+    if b1 > b0:
+        p.eval_many(X, F, G)
+    fullF = D.gather_rows(F, B)
+    fullG = D.gather_rows(G, B)
+    tmax = D.max_over_ranks(1.0 + rank)
+    if rank == 0:
+        np.savez(out_path, F=fullF, G=fullG, tmax=tmax)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_shard_and_gather_equals_single_process(tmp_path, oracle_built):
+    B = 13  # odd on purpose: ranks own 7 and 6 trajectories
+    out = str(tmp_path / "gathered.npz")
+    mp.spawn(_worker, args=(2, _free_port(), B, out), nprocs=2, join=True)
+    got = np.load(out)
+    import tol_b200.synth as synth
+    g = load_golden("S10_skywalker_ts7_gains")
+    p = port_from_golden(g)
+    X = synth.batch(g["x"][0], 4242, 0, B)
+    F, G = np.empty((B, p.neF)), np.empty((B, p.neG))
+    p.eval_many(X, F, G)
+    assert np.array_equal(got["F"], F) and np.array_equal(got["G"], G)
+    assert float(got["tmax"]) == 2.0
+
+
+def test_shard_ranges_cover_the_batch_exactly():
+    import tol_b200.synth as synth
+    for B in (1, 2, 7, 64, 65536, 65537):
+        for w in (1, 2, 4, 8):
+            r = [synth.shard_range(B, q, w) for q in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == B
+            assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+            assert all(b1 >= b0 for b0, b1 in r)
