@@ -343,7 +343,7 @@ def run_ours(args, wl_name):
                    "l2": "%.1f GB touched per step, far larger than the 126 MB L2; no flush needed" % (alg_bytes / 1e9),
                    "inputs": "x0*(1+0.05u)+0.01u', PCG64(seed0+b), seed0=%d (SURVEY.md 8d)" % seed0,
                    "parity_spot_check": checked},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n * B, "d2h_bytes_per_step": 8 * (neF + neG) * B,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n * B * world, "d2h_bytes_per_step": 8 * (neF + neG) * B * world,
                 "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps, "gpu_launches": e2e_launches,
                 "api": "tolcuda_eval_batch(TOLCUDA_HOST_PTRS), pinned host x/F/G"},
         "gpu_launches": launches,

@@ -47,6 +47,7 @@ struct tolcuda_ctx {
     tolcuda_config cfg;
     FgConst c;
     int kernel = 0;
+    int zero_copy = 1;  // single-trajectory path: kernel works on the mapped pinned block (TOLCUDA_ZEROCOPY=0: staged copies)
     int sm_count = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::vector<int> iG, jG;
@@ -184,6 +185,7 @@ int tolcuda_create(const tolcuda_config *cfg, tolcuda_handle *out) {
     pattern_build(c.form, c.ts, h->iG, h->jG);
 
     if (const char *env = std::getenv("TOLCUDA_KERNEL")) h->kernel = std::atoi(env);  // tests / tuning
+    if (const char *env = std::getenv("TOLCUDA_ZEROCOPY")) h->zero_copy = std::atoi(env);
 
     int rc = 0;
     do {
@@ -325,15 +327,24 @@ int tolcuda_eval(tolcuda_handle h, const double *x, int needF, double *F, int ne
     CU(cudaSetDevice(h->cfg.device));
     cudaStream_t st = h->stream;
     std::memcpy(h->h_one + h->ox, x, sizeof(double) * c.n);
-    CU(cudaMemcpyAsync(h->d_one + h->ox, h->h_one + h->ox, sizeof(double) * c.n, cudaMemcpyHostToDevice, st));
-    int rc = launch(h, st, 1, h->d_one + h->ox, c.n, h->d_one + h->oF, c.neF, h->d_one + h->oG, c.neG,
-                    needF > 0, needG > 0);
-    if (rc) return rc;
-    if (needF > 0)
-        CU(cudaMemcpyAsync(h->h_one + h->oF, h->d_one + h->oF, sizeof(double) * c.neF, cudaMemcpyDeviceToHost, st));
-    if (needG > 0)
-        CU(cudaMemcpyAsync(h->h_one + h->oG, h->d_one + h->oG, sizeof(double) * c.neG, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    if (h->zero_copy) {
+        // One launch, no copy commands: the pinned staging block is mapped into the device's address
+        // space (UVA), so the kernel reads x from it and writes F/G into it across PCIe directly.
+        int rc = launch(h, st, 1, h->h_one + h->ox, c.n, h->h_one + h->oF, c.neF, h->h_one + h->oG, c.neG,
+                        needF > 0, needG > 0);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(st));
+    } else {
+        CU(cudaMemcpyAsync(h->d_one + h->ox, h->h_one + h->ox, sizeof(double) * c.n, cudaMemcpyHostToDevice, st));
+        int rc = launch(h, st, 1, h->d_one + h->ox, c.n, h->d_one + h->oF, c.neF, h->d_one + h->oG, c.neG,
+                        needF > 0, needG > 0);
+        if (rc) return rc;
+        if (needF > 0)
+            CU(cudaMemcpyAsync(h->h_one + h->oF, h->d_one + h->oF, sizeof(double) * c.neF, cudaMemcpyDeviceToHost, st));
+        if (needG > 0)
+            CU(cudaMemcpyAsync(h->h_one + h->oG, h->d_one + h->oG, sizeof(double) * c.neG, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
     if (needF > 0) std::memcpy(F, h->h_one + h->oF, sizeof(double) * c.neF);
     if (needG > 0) std::memcpy(G, h->h_one + h->oG, sizeof(double) * c.neG);
     return 0;
