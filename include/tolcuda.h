@@ -9,6 +9,8 @@
 #ifndef TOLCUDA_H_
 #define TOLCUDA_H_
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -56,6 +58,11 @@ typedef struct tolcuda_config {
     double aircraft[15];
     double gains[5];
     double goal[4];
+    /* used only by the set-up queries below (not by F/G):
+     *   limits[8]   = dtmin,dtmax,xmin,xmax,ymin,ymax,zmin,zmax (limits.param file order)
+     *   solver_tol[2] = SNOPT major optimality / feasibility tolerance (snopt.param lines 6, 7) */
+    double limits[8];
+    double solver_tol[2];
 } tolcuda_config;
 
 /* Replaces the problemG7 / problemS10 construction in reference src/tol.cpp:5-36 for the
@@ -87,6 +94,20 @@ int tolcuda_pattern(tolcuda_handle h, int *iGfun, int *jGvar);
 int tolcuda_problem_dims(int formulation, int ts, int *n, int *neF, int *neG);
 int tolcuda_problem_pattern(int formulation, int ts, int *iGfun, int *jGvar);
 
+/* Set-up parity (host only, no CUDA): what the reference constructor leaves in SNOPT's arrays before
+ * runSNOPT -- bit-identical to the reference's.
+ *   initial guess  problemG7::InitialCond src/problemG7.cpp:19-217, problemS10::InitialCond
+ *                  src/problemS10.cpp:19-219          -> x0[n]
+ *   bounds         problem::setLimits src/problem.cpp:198-365 -> xlow,xupp[n], Flow,Fupp[neF]
+ *                  (xstate, xmul, Fmul, Fstate are all zero there)
+ *   solver options problem::runSNOPT src/problem.cpp:1223-1238: Derivative option 1, Iterations
+ *                  limit 60000, tolerances from snopt.param, cold start, ObjRow 0, ObjAdd 0 */
+int tolcuda_problem_initial_guess(const tolcuda_config *cfg, double *x0);
+int tolcuda_problem_bounds(const tolcuda_config *cfg, double *xlow, double *xupp, double *Flow,
+                           double *Fupp);
+/* the configuration a handle was created with (e.g. after tolcuda_create_from_files) */
+int tolcuda_get_config(tolcuda_handle h, tolcuda_config *cfg);
+
 /* One trajectory, host pointers: what reference DEFINEGusrfg_ computes (src/DefineFG.cpp:24-38)
  * without the debug dumps.  Writes F[0..neF) if needF > 0 and G[0..neG) if needG > 0. */
 int tolcuda_eval(tolcuda_handle h, const double *x, int needF, double *F, int needG, double *G);
@@ -97,6 +118,12 @@ int tolcuda_eval(tolcuda_handle h, const double *x, int needF, double *F, int ne
  * every trajectory 128-byte aligned (tolcuda_padded_ld).  flags: TOLCUDA_NEED_* | pointer kind. */
 int tolcuda_eval_batch(tolcuda_handle h, int B, const double *x, long ldx, double *F, long ldF,
                        double *G, long ldG, int flags);
+
+/* page-locked host memory for x/F/G of the host-pointer batch path (full PCIe speed, asynchronous
+ * copies); plain wrappers so that a C/C++ driver needs no CUDA headers */
+int tolcuda_host_alloc(size_t bytes, void **ptr);
+int tolcuda_host_free(void *ptr);
+int tolcuda_device_count(int *count);
 
 /* smallest multiple of 16 doubles (128 bytes) that holds `len` doubles */
 long tolcuda_padded_ld(long len);

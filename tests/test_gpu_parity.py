@@ -204,3 +204,34 @@ def test_full_size_properties(name, seed0, B, oracle_built):
     assert_parity(F[torch.from_numpy(rows).cuda(), :p.neF].cpu().numpy(), Fr, name + " sample F")
     assert_parity(G[torch.from_numpy(rows).cuda(), :p.neG].cpu().numpy(), Gr, name + " sample G")
     ev.close()
+
+
+def test_tolbatch_driver_end_to_end(tmp_path):
+    """the C++ batch driver (reference CLI arguments + reference .param files -> initial guess ->
+    perturbed batch -> all visible GPUs -> host gather): trajectory 0 is the reference's x0, so its
+    objective must equal the reference's F[0]; every value finite; 2 runs agree bit for bit"""
+    import json
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "tol_b200", "tolbatch")
+    root = os.path.join(ROOT, "oracle", "_ref", "params")
+    if not os.path.isdir(root):
+        root = "/root/reference"
+    if not (os.path.exists(exe) and os.path.isdir(os.path.join(root, "aircraft"))):
+        pytest.skip("tolbatch or the reference .param files are not present")
+    for args, fixture in ((["0", "0", "70", "0", "-100", "0", "100", "tempest", "S10"], "S10_tempest_ts100"),
+                          (["0", "0", "70", "400", "0", "0", "0", "skywalker", "G7"], "G7_skywalker_ts100")):
+        g = load_golden(fixture)
+        outs = []
+        for run in range(2):
+            js = str(tmp_path / ("r%d.json" % run))
+            r = subprocess.run([exe] + args + ["--root", root, "--batch", "300", "--steps", "1", "--json", js],
+                               capture_output=True, text=True, timeout=120)
+            assert r.returncode == 0, r.stdout + r.stderr
+            outs.append(json.load(open(js)))
+        d = outs[0]
+        assert (d["n"], d["neF"], d["neG"], d["nonfinite"]) == (int(g["n"]), int(g["neF"]), int(g["neG"]), 0)
+        f0 = d["trajectories"][0]["objective"]
+        assert abs(f0 - g["F"][0, 0]) <= 1e-14 + 1e-12 * abs(g["F"][0, 0])
+        assert outs[0]["trajectories"] == outs[1]["trajectories"]

@@ -95,3 +95,25 @@ def test_synthetic_batch_is_shard_invariant():
     assert np.array_equal(full, np.concatenate(parts))
     # fixture sample s >= 1 is perturb(x0, seed0 + s - 1)
     assert np.array_equal(g["x"][1], T.synth.perturb(x0, int(g["seed0"])))
+
+
+def _cfg_from_golden(g):
+    lm = g["lm"]  # member order dtmin,dtmax,xmax,ymax,zmax,xmin,ymin,zmin -> file order
+    limits = [lm[0], lm[1], lm[5], lm[2], lm[6], lm[3], lm[7], lm[4]]
+    return T.make_config(str(g["mission"]), int(g["ts"]), g["ac"], g["gn"], g["goal_ned"],
+                         limits=limits, solver_tol=g["sn"][4:6])
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_initial_guess_is_bit_identical_to_reference_initialcond(name):
+    g = load_golden(name)
+    x0 = T.initial_guess(_cfg_from_golden(g))
+    assert np.array_equal(x0, g["x"][0]), np.abs(x0 - g["x"][0]).max()
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_bounds_are_bit_identical_to_reference_setlimits(name):
+    g = load_golden(name)
+    xl, xu, fl, fu = T.bounds(_cfg_from_golden(g))
+    for got, key in ((xl, "xlow"), (xu, "xupp"), (fl, "Flow"), (fu, "Fupp")):
+        assert np.array_equal(got, g[key]), key

@@ -1,0 +1,193 @@
+// tolbatch -- batch driver over libtolcuda: the counterpart of the reference's CLI `tol E N U Eg Ng Ug Rg
+// aircraft mission` (src/tol.cpp:38-53, src/arguments.cpp:32-46), which builds ONE problem and hands it to
+// SNOPT.  tolbatch builds the same problem from the same positional arguments and the same .param files,
+// takes the reference's initial guess, spreads B perturbed copies of it (or B trajectories read from a
+// file) over the GPUs of the box by trajectory index, evaluates F and G for all of them through
+// tolcuda_eval_batch, gathers the rows in one pinned host buffer and reports throughput plus a
+// per-trajectory summary.  It uses nothing but the C ABI of include/tolcuda.h.
+//
+//   tolbatch E N U Eg Ng Ug Rg aircraft mission [--root DIR/] [--ts N] [--batch B] [--gpus G]
+//            [--seed S] [--perturb REL,ABS] [--x-file raw_f64] [--steps K] [--json out.json]
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/tolcuda.h"
+
+namespace {
+
+struct Args {
+    double enu[3] = {0, 0, 0}, goal[4] = {0, 0, 0, 0};
+    std::string aircraft, mission, root = "./", xfile, json;
+    int ts = 0, batch = 4096, gpus = 0, steps = 3;
+    uint64_t seed = 1;
+    double rel = 0.05, abs_ = 0.01;
+};
+
+// splitmix64: one independent stream per trajectory index, so the batch does not depend on the sharding
+struct Rng {
+    uint64_t s;
+    explicit Rng(uint64_t seed) : s(seed) {}
+    uint64_t next() {
+        uint64_t z = (s += 0x9e3779b97f4a7c15ULL);
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+        return z ^ (z >> 31);
+    }
+    double sym() { return 2.0 * ((next() >> 11) * (1.0 / 9007199254740992.0)) - 1.0; }  // U(-1, 1)
+};
+
+void die(const std::string &msg) {
+    std::fprintf(stderr, "tolbatch: %s\n", msg.c_str());
+    std::exit(2);
+}
+
+void check(int rc, const char *what) {
+    if (rc) die(std::string(what) + " failed (" + std::to_string(rc) + "): " + tolcuda_last_error());
+}
+
+Args parse(int argc, char **argv) {
+    if (argc < 10)
+        die("usage: tolbatch E N U Eg Ng Ug Rg aircraft mission [--root DIR/] [--ts N] [--batch B] [--gpus G] "
+            "[--seed S] [--perturb REL,ABS] [--x-file F] [--steps K] [--json OUT]");
+    Args a;
+    for (int i = 0; i < 3; i++) a.enu[i] = std::atof(argv[1 + i]);  // as src/arguments.cpp:35-41 (atof)
+    for (int i = 0; i < 4; i++) a.goal[i] = std::atof(argv[4 + i]);
+    a.aircraft = argv[8];
+    a.mission = argv[9];
+    for (int i = 10; i < argc; i++) {
+        const std::string k = argv[i];
+        auto val = [&]() -> const char * {
+            if (i + 1 >= argc) die("missing value after " + k);
+            return argv[++i];
+        };
+        if (k == "--root") a.root = val();
+        else if (k == "--ts") a.ts = std::atoi(val());
+        else if (k == "--batch") a.batch = std::atoi(val());
+        else if (k == "--gpus") a.gpus = std::atoi(val());
+        else if (k == "--steps") a.steps = std::atoi(val());
+        else if (k == "--seed") a.seed = std::strtoull(val(), nullptr, 10);
+        else if (k == "--x-file") a.xfile = val();
+        else if (k == "--json") a.json = val();
+        else if (k == "--perturb") {
+            if (std::sscanf(val(), "%lf,%lf", &a.rel, &a.abs_) != 2) die("--perturb wants REL,ABS");
+        } else die("unknown option " + k);
+    }
+    if (!a.root.empty() && a.root.back() != '/') a.root += '/';  // the reference concatenates paths
+    return a;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    const Args a = parse(argc, argv);
+    int ndev = 0;
+    check(tolcuda_device_count(&ndev), "device query");
+    const int G = a.gpus > 0 ? a.gpus : ndev;
+    if (G < 1 || G > ndev) die("asked for " + std::to_string(G) + " GPUs, " + std::to_string(ndev) + " present");
+
+    std::vector<tolcuda_handle> h(G, nullptr);
+    for (int g = 0; g < G; g++)
+        check(tolcuda_create_from_files(a.root.c_str(), a.aircraft.c_str(), a.mission.c_str(), a.enu[0], a.enu[1],
+                                        a.enu[2], a.goal[0], a.goal[1], a.goal[2], a.goal[3], a.ts, g, &h[g]),
+              "tolcuda_create_from_files");
+    int n, neF, neG;
+    check(tolcuda_dims(h[0], &n, &neF, &neG), "tolcuda_dims");
+    tolcuda_config cfg;
+    check(tolcuda_get_config(h[0], &cfg), "tolcuda_get_config");
+    const int ts = cfg.ts, B = a.batch;
+    const long ldx = tolcuda_padded_ld(n), ldF = tolcuda_padded_ld(neF), ldG = tolcuda_padded_ld(neG);
+    std::printf("TOLBATCH: %s / %s, ts=%d, n=%d neF=%d neG=%d, %d trajectories on %d GPU(s)\n", a.mission.c_str(),
+                a.aircraft.c_str(), ts, n, neF, neG, B, G);
+
+    double *X, *F, *Gv;
+    check(tolcuda_host_alloc(sizeof(double) * ldx * B, (void **)&X), "pinned x");
+    check(tolcuda_host_alloc(sizeof(double) * ldF * B, (void **)&F), "pinned F");
+    check(tolcuda_host_alloc(sizeof(double) * ldG * B, (void **)&Gv), "pinned G");
+
+    // inputs: the reference's initial trajectory, perturbed per trajectory index, or a raw float64 file
+    std::vector<double> x0(n);
+    check(tolcuda_problem_initial_guess(&cfg, x0.data()), "initial guess");
+    if (!a.xfile.empty()) {
+        FILE *f = std::fopen(a.xfile.c_str(), "rb");
+        if (!f) die("cannot open " + a.xfile);
+        for (int b = 0; b < B; b++)
+            if (std::fread(X + (size_t)b * ldx, sizeof(double), n, f) != (size_t)n) die("short read from " + a.xfile);
+        std::fclose(f);
+    } else {
+        for (int b = 0; b < B; b++) {
+            Rng r(a.seed * 0x100000001b3ULL + (uint64_t)b);
+            double *xb = X + (size_t)b * ldx;
+            for (int i = 0; i < n; i++) {
+                const double u = r.sym(), up = r.sym();
+                xb[i] = b == 0 ? x0[i] : x0[i] * (1.0 + a.rel * u) + a.abs_ * up;  // trajectory 0 is x0 itself
+            }
+        }
+    }
+
+    // evaluate: one host thread per device, contiguous block of trajectory indices each, no collective
+    std::vector<double> secs(G, 0.0);
+    double best = 1e300;
+    for (int step = 0; step < a.steps; step++) {
+        std::vector<std::thread> th;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int g = 0; g < G; g++)
+            th.emplace_back([&, g]() {
+                const int per = (B + G - 1) / G, b0 = std::min(B, g * per), b1 = std::min(B, b0 + per);
+                const auto s0 = std::chrono::steady_clock::now();
+                if (b1 > b0)
+                    check(tolcuda_eval_batch(h[g], b1 - b0, X + (size_t)b0 * ldx, ldx, F + (size_t)b0 * ldF, ldF,
+                                             Gv + (size_t)b0 * ldG, ldG, TOLCUDA_NEED_F | TOLCUDA_NEED_G | TOLCUDA_HOST_PTRS),
+                          "tolcuda_eval_batch");
+                secs[g] = std::chrono::duration<double>(std::chrono::steady_clock::now() - s0).count();
+            });
+        for (auto &t : th) t.join();
+        const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        best = std::min(best, wall);
+        std::printf("TOLBATCH: step %d: %.3f ms wall, %.4g node-evals/s end to end (host x -> host F,G)\n", step,
+                    1e3 * wall, (double)B * ts / wall);
+    }
+
+    // per-trajectory summary: objective, worst defect, worst boundary violation, finiteness
+    const int nb = cfg.formulation == TOLCUDA_G7 ? 12 : 11;
+    long nonfinite = 0;
+    double worst_defect = 0.0;
+    std::vector<double> obj(B), defect(B), bnd(B);
+    for (int b = 0; b < B; b++) {
+        const double *Fb = F + (size_t)b * ldF, *Gb = Gv + (size_t)b * ldG;
+        double d = 0.0, e = 0.0;
+        for (int i = 1; i < neF - nb; i++) d = std::fmax(d, std::fabs(Fb[i]));
+        for (int i = neF - nb; i < neF; i++) e = std::fmax(e, std::fabs(Fb[i]));
+        for (int i = 0; i < neF; i++) nonfinite += !std::isfinite(Fb[i]);
+        for (int i = 0; i < neG; i++) nonfinite += !std::isfinite(Gb[i]);
+        obj[b] = Fb[0], defect[b] = d, bnd[b] = e;
+        worst_defect = std::fmax(worst_defect, d);
+    }
+    std::printf("TOLBATCH: best %.3f ms, %.4g node-evals/s; F[0] of trajectory 0 = %.17g; worst defect %.6g; "
+                "non-finite values %ld\n",
+                1e3 * best, (double)B * ts / best, obj[0], worst_defect, nonfinite);
+
+    if (!a.json.empty()) {
+        FILE *f = std::fopen(a.json.c_str(), "w");
+        if (!f) die("cannot write " + a.json);
+        std::fprintf(f, "{\n \"mission\": \"%s\", \"aircraft\": \"%s\", \"ts\": %d, \"n\": %d, \"neF\": %d, \"neG\": %d,\n",
+                     a.mission.c_str(), a.aircraft.c_str(), ts, n, neF, neG);
+        std::fprintf(f, " \"batch\": %d, \"gpus\": %d, \"best_ms\": %.6f, \"node_evals_per_s\": %.6g, \"nonfinite\": %ld,\n", B, G,
+                     1e3 * best, (double)B * ts / best, nonfinite);
+        std::fprintf(f, " \"trajectories\": [\n");
+        for (int b = 0; b < B; b++)
+            std::fprintf(f, "  {\"b\": %d, \"objective\": %.17g, \"max_abs_defect\": %.17g, \"max_abs_boundary\": %.17g}%s\n", b,
+                         obj[b], defect[b], bnd[b], b + 1 < B ? "," : "");
+        std::fprintf(f, " ]\n}\n");
+        std::fclose(f);
+    }
+    for (int g = 0; g < G; g++) tolcuda_destroy(h[g]);
+    tolcuda_host_free(X), tolcuda_host_free(F), tolcuda_host_free(Gv);
+    return nonfinite ? 1 : 0;
+}

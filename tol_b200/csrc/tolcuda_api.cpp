@@ -117,6 +117,23 @@ const char *tolcuda_version(void) { return TOLCUDA_VERSION; }
 
 long tolcuda_padded_ld(long len) { return round_up(len, 16); }
 
+int tolcuda_host_alloc(size_t bytes, void **ptr) {
+    if (!ptr) return TOLCUDA_EINVAL;
+    CU(cudaMallocHost(ptr, bytes));
+    return 0;
+}
+
+int tolcuda_host_free(void *ptr) {
+    if (ptr) CU(cudaFreeHost(ptr));
+    return 0;
+}
+
+int tolcuda_device_count(int *count) {
+    if (!count) return TOLCUDA_EINVAL;
+    CU(cudaGetDeviceCount(count));
+    return 0;
+}
+
 int tolcuda_read_params(const char *path, double *values, int cap, int *count) {
     if (!path || !count) return TOLCUDA_EINVAL;
     std::vector<double> v;
@@ -235,6 +252,9 @@ int tolcuda_create_from_files(const char *root, const char *aircraft, const char
     if ((e = read_gains(root, ms, cfg.gains))) return e;
     double sn[6];
     if ((e = read_snopt(root, ms, sn))) return e;
+    if ((e = read_limits(root, ms, cfg.limits))) return e;
+    cfg.solver_tol[0] = sn[4];
+    cfg.solver_tol[1] = sn[5];
     const int nb = cfg.formulation == TOLCUDA_G7 ? 12 : 11;
     if ((int)sn[1] != TOLCUDA_PX || (int)sn[2] != TOLCUDA_PF || (int)sn[3] != nb) {
         set_error("snopt.param: numinp/numstates/numbounds differ from the built formulation");
@@ -296,6 +316,29 @@ int tolcuda_problem_pattern(int formulation, int ts, int *iGfun, int *jGvar) {
     pattern_build(formulation, ts, iG, jG);
     std::memcpy(iGfun, iG.data(), sizeof(int) * iG.size());
     std::memcpy(jGvar, jG.data(), sizeof(int) * jG.size());
+    return 0;
+}
+
+static bool config_ok(const tolcuda_config *cfg) {
+    return cfg && (cfg->formulation == TOLCUDA_G7 || cfg->formulation == TOLCUDA_S10) && cfg->ts >= 1;
+}
+
+int tolcuda_problem_initial_guess(const tolcuda_config *cfg, double *x0) {
+    if (!config_ok(cfg) || !x0) return TOLCUDA_EINVAL;
+    initial_guess(*cfg, x0);
+    return 0;
+}
+
+int tolcuda_problem_bounds(const tolcuda_config *cfg, double *xlow, double *xupp, double *Flow,
+                           double *Fupp) {
+    if (!config_ok(cfg) || !xlow || !xupp || !Flow || !Fupp) return TOLCUDA_EINVAL;
+    bounds(*cfg, xlow, xupp, Flow, Fupp);
+    return 0;
+}
+
+int tolcuda_get_config(tolcuda_handle h, tolcuda_config *cfg) {
+    if (!h || !cfg) return TOLCUDA_EINVAL;
+    *cfg = h->cfg;
     return 0;
 }
 

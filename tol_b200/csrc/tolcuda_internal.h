@@ -21,6 +21,9 @@ void set_error(const std::string &msg);
 void pattern_dims(int form, int ts, int *n, int *neF, int *neG, int *R0, int *nbG);
 void pattern_build(int form, int ts, std::vector<int> &iG, std::vector<int> &jG);
 
+void initial_guess(const tolcuda_config &cfg, double *x);
+void bounds(const tolcuda_config &cfg, double *xlow, double *xupp, double *Flow, double *Fupp);
+
 int read_params(const std::string &path, std::vector<double> &out);
 int read_aircraft(const std::string &root, const std::string &name, double ac[15]);
 int read_gains(const std::string &root, const std::string &mission, double gn[5]);

@@ -42,6 +42,33 @@ def read_params(path, cap=64):
     return v[:min(cnt.value, cap)].copy(), cnt.value
 
 
+def make_config(mission, ts, aircraft, gains, goal_ned, wind_model=1, device=0, limits=None, solver_tol=None):
+    cfg = _l.Config()
+    cfg.formulation, cfg.ts, cfg.wind_model, cfg.device = _FORM[mission], int(ts), int(wind_model), int(device)
+    cfg.aircraft[:] = [float(v) for v in aircraft]
+    cfg.gains[:] = [float(v) for v in gains]
+    cfg.goal[:] = [float(v) for v in goal_ned]
+    cfg.limits[:] = [float(v) for v in (limits if limits is not None else [0.0] * 8)]
+    cfg.solver_tol[:] = [float(v) for v in (solver_tol if solver_tol is not None else [0.0, 0.0])]
+    return cfg
+
+
+def initial_guess(cfg):
+    """reference InitialCond: x0[n] (host only)"""
+    n, _, _ = problem_dims(cfg.formulation, cfg.ts)
+    x0 = np.empty(n)
+    _l.check(_l.load().tolcuda_problem_initial_guess(C.byref(cfg), _dp(x0)))
+    return x0
+
+
+def bounds(cfg):
+    """reference setLimits: xlow, xupp, Flow, Fupp (host only)"""
+    n, neF, _ = problem_dims(cfg.formulation, cfg.ts)
+    xl, xu, fl, fu = np.empty(n), np.empty(n), np.empty(neF), np.empty(neF)
+    _l.check(_l.load().tolcuda_problem_bounds(C.byref(cfg), _dp(xl), _dp(xu), _dp(fl), _dp(fu)))
+    return xl, xu, fl, fu
+
+
 def padded_ld(n):
     return int(_l.load().tolcuda_padded_ld(int(n)))
 
@@ -49,11 +76,7 @@ def padded_ld(n):
 class Evaluator:
     def __init__(self, mission, ts, aircraft, gains, goal_ned, wind_model=1, device=0):
         L = _l.load()
-        cfg = _l.Config()
-        cfg.formulation, cfg.ts, cfg.wind_model, cfg.device = _FORM[mission], int(ts), int(wind_model), int(device)
-        cfg.aircraft[:] = [float(v) for v in aircraft]
-        cfg.gains[:] = [float(v) for v in gains]
-        cfg.goal[:] = [float(v) for v in goal_ned]
+        cfg = make_config(mission, ts, aircraft, gains, goal_ned, wind_model, device)
         self.h = C.c_void_p()
         _l.check(L.tolcuda_create(C.byref(cfg), C.byref(self.h)))
         self._finish(L, device)

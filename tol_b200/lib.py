@@ -17,7 +17,7 @@ class Config(C.Structure):
     """struct tolcuda_config"""
     _fields_ = [("formulation", C.c_int), ("ts", C.c_int), ("wind_model", C.c_int),
                 ("device", C.c_int), ("aircraft", C.c_double * 15), ("gains", C.c_double * 5),
-                ("goal", C.c_double * 4)]
+                ("goal", C.c_double * 4), ("limits", C.c_double * 8), ("solver_tol", C.c_double * 2)]
 
 
 _lib = None
@@ -40,8 +40,14 @@ def load():
     L.tolcuda_pattern.argtypes = [vp, ip, ip]
     L.tolcuda_problem_dims.argtypes = [C.c_int, C.c_int, ip, ip, ip]
     L.tolcuda_problem_pattern.argtypes = [C.c_int, C.c_int, ip, ip]
+    L.tolcuda_problem_initial_guess.argtypes = [C.POINTER(Config), dp]
+    L.tolcuda_problem_bounds.argtypes = [C.POINTER(Config), dp, dp, dp, dp]
+    L.tolcuda_get_config.argtypes = [vp, C.POINTER(Config)]
     L.tolcuda_eval.argtypes = [vp, dp, C.c_int, dp, C.c_int, dp]
     L.tolcuda_eval_batch.argtypes = [vp, C.c_int, vp, C.c_long, vp, C.c_long, vp, C.c_long, C.c_int]
+    L.tolcuda_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.tolcuda_host_free.argtypes = [vp]
+    L.tolcuda_device_count.argtypes = [ip]
     L.tolcuda_padded_ld.argtypes = [C.c_long]
     L.tolcuda_padded_ld.restype = C.c_long
     L.tolcuda_set_stream.argtypes = [vp, vp]
