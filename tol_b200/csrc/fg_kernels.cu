@@ -649,20 +649,20 @@ cudaError_t launch_warp(const FgLaunch &L) {
 
 template <int FORM, int WIND>
 cudaError_t launch_any(const FgLaunch &L) {
-    if (L.kernel == 2) return launch_warp<FORM, WIND, 4, 4>(L);  // 128 registers, 16 warps / SM
-    // kernel A; register budget per block-size class = 65536 / (MAXT * MINB)
+    // Kernel A (one CTA per trajectory) needs the whole trajectory in one CTA at a register budget that
+    // does not spill: ts <= 256.  Longer trajectories, and L.kernel == 2, take kernel B, whose warps walk
+    // the tiles of a trajectory one after the other (any ts).
     const int ts = L.c->ts;
-    if (ts <= 128) return launch_cta<FORM, WIND, 128, 4>(L);
-    if (ts <= 256) return launch_cta<FORM, WIND, 256, 2>(L);
-    if (ts <= 512) return launch_cta<FORM, WIND, 512, 1>(L);
-    return launch_cta<FORM, WIND, 1024, 1>(L);
+    if (L.kernel == 2 || ts > 256) return launch_warp<FORM, WIND, 4, 4>(L);  // 128 registers, 16 warps / SM
+    if (ts <= 128) return launch_cta<FORM, WIND, 128, 4>(L);                 // 128 registers, 16 warps / SM
+    return launch_cta<FORM, WIND, 256, 2>(L);                                // 128 registers, 14-16 warps / SM
 }
 
 }  // namespace
 
 cudaError_t fg_launch(const FgLaunch &L) {
     if (L.B <= 0) return cudaSuccess;
-    if (!L.c || L.c->ts < 1 || L.c->ts > 1024) return cudaErrorInvalidValue;
+    if (!L.c || L.c->ts < 1) return cudaErrorInvalidValue;
     if (L.c->form == TOLCUDA_FORM_S10) {
         if (L.c->wind == 1) return launch_any<TOLCUDA_FORM_S10, 1>(L);
         if (L.c->wind == 0) return launch_any<TOLCUDA_FORM_S10, 0>(L);

@@ -158,8 +158,8 @@ int tolcuda_create(const tolcuda_config *cfg, tolcuda_handle *out) {
         set_error("wind model not built (0 = none, 1 = linear boundary layer)");
         return TOLCUDA_EUNSUPPORTED;
     }
-    if (cfg->ts < 1 || cfg->ts > 1024) {
-        set_error("ts must be in 1..1024 (one CTA owns one trajectory)");
+    if (cfg->ts < 1 || cfg->ts > 1000000) {
+        set_error("ts must be in 1..1000000");
         return TOLCUDA_EUNSUPPORTED;
     }
     tolcuda_ctx *h = new (std::nothrow) tolcuda_ctx();

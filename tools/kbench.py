@@ -20,6 +20,7 @@ ap.add_argument("--batch", type=int, default=16384)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--kernel", type=int, default=0)
+ap.add_argument("--goff", type=int, default=0, help="shift the G buffer by this many doubles (alignment experiments)")
 ap.add_argument("--need", default="FG")
 ap.add_argument("--distinct", type=int, default=512, help="distinct synthetic trajectories (tiled)")
 args = ap.parse_args()
@@ -38,7 +39,7 @@ Xu = torch.zeros(U, ldx, dtype=torch.float64)
 T.synth.batch(g["x"][0], seed0, 0, U, out=Xu.numpy())
 Xd = Xu.cuda()[torch.arange(B, device="cuda") % U].contiguous()
 Fd = torch.empty(B, ldF, dtype=torch.float64, device="cuda")
-Gd = torch.empty(B, ldG, dtype=torch.float64, device="cuda")
+Gd = torch.empty(B * ldG + 64, dtype=torch.float64, device="cuda")[args.goff:args.goff + B * ldG].view(B, ldG)
 st = torch.cuda.Stream()
 ev.set_stream(st.cuda_stream)
 needF, needG = "F" in args.need, "G" in args.need
@@ -56,6 +57,6 @@ with torch.cuda.stream(st):
     torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / args.steps
 by = 8.0 * B * (n + (neF if needF else 0) + (neG if needG else 0))
-print(json.dumps({"workload": args.workload, "B": B, "kernel": args.kernel, "need": args.need, "ms": ms,
+print(json.dumps({"workload": args.workload, "B": B, "kernel": args.kernel, "goff": args.goff, "need": args.need, "ms": ms,
                   "node_evals_per_s": B * ts / (ms * 1e-3), "GBps": by / ms / 1e6,
                   "frac_of_6544": by / ms / 1e6 / 6544.0}))
