@@ -23,6 +23,7 @@ extern "C" {
  * reference runs whenever its MongoDB wind server is unreachable, src/problem.cpp:63-78) */
 #define TOLCUDA_WIND_NONE 0
 #define TOLCUDA_WIND_LINEAR_LAYER 1
+#define TOLCUDA_WIND_CUBE 3 /* modelWind case 3 (src/problem.cpp:544-695); set with tolcuda_set_wind_grid */
 
 /* error codes (negative; positive values are cudaError_t) */
 #define TOLCUDA_EINVAL (-1)      /* bad argument                                         */
@@ -78,6 +79,19 @@ int tolcuda_create_from_files(const char *root, const char *aircraft, const char
                               double east, double north, double up, double east_goal,
                               double north_goal, double up_goal, double radius_goal,
                               int ts_override, int device, tolcuda_handle *out);
+
+/* Wind model 3 of the reference: the wind cube that reference cacheWind pulls from its MongoDB server
+ * (src/problem.cpp:371-460: cache[i][j][k], i < ne, j < nn, k < nu) is handed over by the caller and kept in
+ * device memory; the F/G kernels then interpolate it per node exactly as modelWind case 3 does
+ * (src/problem.cpp:544-695: trilinear shape functions of the v component and of its gradient; u, w stay 0).
+ *   gx[ne], gy[nn], gz[nu]  grid coordinates = cache[i][0][0].x, cache[0][j][0].y, cache[0][0][k].z (ENU, m)
+ *   v[ne*nn*nu]             cache[i][j][k].v, i-major
+ *   datum[3]                EastFromDatum, NorthFromDatum, UpFromDatum (src/problem.cpp:406-413)
+ *   spacing[3]              xspacing, yspacing, zspacing (include/problem.h:87-89: 150 m each)
+ * Switches the context to TOLCUDA_WIND_CUBE.  Nodes outside the cube use the nearest cell (the reference
+ * indexes out of bounds there). */
+int tolcuda_set_wind_grid(tolcuda_handle h, int ne, int nn, int nu, const double *gx, const double *gy,
+                          const double *gz, const double *v, const double *datum, const double *spacing);
 
 int tolcuda_destroy(tolcuda_handle h);
 

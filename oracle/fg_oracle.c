@@ -133,6 +133,70 @@ static void model_wind(const tolo_problem *p, const double *x, tolo_wind *W) {
             W->dv_dz[i] = -Vref / href;        /* :524 */
         }
     }
+    if (p->wind_model == 3) { /* src/problem.cpp:544-695: trilinear interpolation of v and its gradient */
+        const int nn = p->grid_nn, nu = p->grid_nu;
+        const double dx = p->spacing[0], dy = p->spacing[1], dz = p->spacing[2];
+#define GV(i, j, k) p->grid_v[((size_t)(i) * nn + (j)) * nu + (k)]
+        for (int ii = 0; ii < nodes; ii++) {
+            const double xs = x[ii * p->numinp + 2] + p->datum[0]; /* :551-553, ENU <- NED */
+            const double ys = x[ii * p->numinp + 1] + p->datum[1];
+            const double zs = -x[ii * p->numinp + 3] + p->datum[2];
+            int xi, yi, zi;
+            /* :556-572.  (sic) the x search runs to cache_north and the y search to cache_east */
+            for (xi = 0; xi < p->grid_nn; xi++)
+                if ((xs - p->grid_x[xi]) < dx) break;
+            for (yi = 0; yi < p->grid_ne; yi++)
+                if ((ys - p->grid_y[yi]) < dy) break;
+            for (zi = 0; zi < p->grid_nu; zi++)
+                if ((zs - p->grid_z[zi]) < dz) break;
+            double vc[8];
+            vc[0] = GV(xi, yi, zi), vc[1] = GV(xi + 1, yi, zi), vc[2] = GV(xi, yi + 1, zi);
+            vc[3] = GV(xi + 1, yi + 1, zi), vc[4] = GV(xi, yi, zi + 1), vc[5] = GV(xi + 1, yi, zi + 1);
+            vc[6] = GV(xi, yi + 1, zi + 1), vc[7] = GV(xi + 1, yi + 1, zi + 1);
+            const double xrel = (xs - p->grid_x[xi]), yrel = (ys - p->grid_y[yi]), zrel = (zs - p->grid_z[zi]);
+            const double zeta = xrel / dx, eta = yrel / dy, mu = zrel / dz;
+            double N[8], NX[8], NY[8], NZ[8];
+            N[0] = (1 - zeta) * (1 - eta) * (1 - mu); /* :618-625 */
+            N[1] = zeta * (1 - eta) * (1 - mu);
+            N[2] = (1 - zeta) * eta * (1 - mu);
+            N[3] = zeta * eta * (1 - mu);
+            N[4] = (1 - zeta) * (1 - eta) * mu;
+            N[5] = zeta * (1 - eta) * mu;
+            N[6] = (1 - zeta) * eta * mu;
+            N[7] = zeta * eta * mu;
+            NX[0] = -((yrel / dy - 1.0) * (zrel / dz - 1.0)) / dx; /* :643-650 */
+            NX[1] = ((yrel / dy - 1.0) * (zrel / dz - 1.0)) / dx;
+            NX[2] = (yrel * (zrel / dz - 1.0)) / (dx * dy);
+            NX[3] = -(yrel * (zrel / dz - 1.0)) / (dx * dy);
+            NX[4] = (zrel * (yrel / dy - 1.0)) / (dx * dz);
+            NX[5] = -(zrel * (yrel / dy - 1.0)) / (dx * dz);
+            NX[6] = -(yrel * zrel) / (dx * dy * dz);
+            NX[7] = (yrel * zrel) / (dx * dy * dz);
+            NY[0] = -((xrel / dx - 1.0) * (zrel / dz - 1.0)) / dy; /* :653-660 */
+            NY[1] = (xrel * (zrel / dz - 1.0)) / (dx * dy);
+            NY[2] = ((xrel / dx - 1.0) * (zrel / dz - 1.0)) / dy;
+            NY[3] = -(xrel * (zrel / dz - 1.0)) / (dx * dy);
+            NY[4] = (zrel * (xrel / dx - 1.0)) / (dy * dz);
+            NY[5] = -(xrel * zrel) / (dx * dy * dz);
+            NY[6] = -(zrel * (xrel / dx - 1.0)) / (dy * dz);
+            NY[7] = (xrel * zrel) / (dx * dy * dz);
+            NZ[0] = -((xrel / dx - 1.0) * (yrel / dy - 1.0)) / dz; /* :663-670 */
+            NZ[1] = (xrel * (yrel / dy - 1.0)) / (dx * dz);
+            NZ[2] = (yrel * (xrel / dx - 1.0)) / (dy * dz);
+            NZ[3] = -(xrel * yrel) / (dx * dy * dz);
+            NZ[4] = ((xrel / dx - 1.0) * (yrel / dy - 1.0)) / dz;
+            NZ[5] = -(xrel * (yrel / dy - 1.0)) / (dx * dz);
+            NZ[6] = -(yrel * (xrel / dx - 1.0)) / (dy * dz);
+            NZ[7] = (xrel * yrel) / (dx * dy * dz);
+            for (int i = 0; i < 8; i++) { /* :631-635, :682-692: only v is interpolated */
+                W->v[ii] += N[i] * vc[i];
+                W->dv_dx[ii] += NX[i] * vc[i];
+                W->dv_dy[ii] += NY[i] * vc[i];
+                W->dv_dz[ii] += NZ[i] * vc[i];
+            }
+        }
+#undef GV
+    }
 }
 
 /* ------------------------------------------------- per-node shared sub-expressions (F and G) --- */

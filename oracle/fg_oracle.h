@@ -23,11 +23,18 @@ typedef struct tolo_problem {
     int numinp;      /* px = 11                                  (src/parameters.cpp:140)      */
     int numstates;   /* pF = 8                                   (src/parameters.cpp:141)      */
     int numbounds;   /* 12 (G7) | 11 (S10)                       (src/parameters.cpp:142)      */
-    int wind_model;  /* Pwindmodel: 0 none, 1 linear layer       (src/problem.cpp:475-531)     */
+    int wind_model;  /* Pwindmodel: 0 none, 1 linear layer, 3 cube (src/problem.cpp:475-695)   */
     double mm, SS, ee, AR, Cd0; /* aircraft                      (src/parameters.cpp:48-53)    */
     double kT, kp, kv, kdt;     /* gains                         (src/parameters.cpp:83-87)    */
     double xg, yg, rg;          /* goal, NED                     (src/problem.cpp:24-27)       */
     double chi_d;               /* G7 course angle               (src/problemG7.cpp:524)       */
+    /* wind model 3 only: the cached wind cube of src/problem.cpp:443-459 (cache[i][j][k], i < ne,
+     * j < nn, k < nu), of which modelWind case 3 (:544-695) interpolates the v component alone */
+    int grid_ne, grid_nn, grid_nu;
+    const double *grid_x, *grid_y, *grid_z; /* cache[i][0][0].x, cache[0][j][0].y, cache[0][0][k].z    */
+    const double *grid_v;                   /* cache[i][j][k].v, i-major                               */
+    double datum[3];                        /* EastFromDatum, NorthFromDatum, UpFromDatum              */
+    double spacing[3];                      /* xspacing, yspacing, zspacing (include/problem.h:87-89)  */
 } tolo_problem;
 
 /* n, neF as src/problem.cpp:151-152; neG by counting the pattern walk */

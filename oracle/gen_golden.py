@@ -48,9 +48,60 @@ CASES = [
 ]
 
 
+# Wind model 3 (src/problem.cpp:544-695) needs the reference's MongoDB wind server; here the UNMODIFIED
+# reference is driven into it by filling its protected wind cache from the harness (ref_driver.cpp:
+# tolref_set_wind_grid) with a synthetic, seeded wind cube.  Sample 3+ is also shifted so that the
+# trajectory crosses cell boundaries.
+WIND3 = {
+    "S10_tempest_ts100_wind3": ("S10", "tempest", (0, 0, 70), (0, -100, 0, 100), None, None, 31, 5),
+    "G7_skywalker_ts45_wind3": ("G7", "skywalker", (0, 0, 70), (400, 0, 0, 0), 45, (100, 3, 2, 0, 0.5), 32, 5),
+    "S10_tempestwill_ts7_wind3": ("S10", "tempest_will", (0, 0, 70), (30, 40, 0, 50), 7, None, 33, 5),
+}
+
+
+def wind_cube(seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    gx = np.arange(-750.0, 751.0, 150.0) + 17400.0   # EastFromDatum override, src/problem.cpp:411-413
+    gy = np.arange(-750.0, 751.0, 150.0) + 25800.0
+    gz = np.array([0.0, 150.0, 300.0, 450.0])
+    uvw = rng.normal(0.0, 3.0, (gx.size, gy.size, gz.size, 3))
+    return gx, gy, gz, uvw, np.array([17400.0, 25800.0, 200.0]), np.array([150.0, 150.0, 150.0])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     index = {}
+    for name, (mission, ac, enu, goal, ts, gains, seed0, ns) in WIND3.items():
+        p = R.RefProblem(mission, ac, enu, goal, ts=ts, gains=gains)
+        prm = p.params()
+        gx, gy, gz, uvw, datum, spacing = wind_cube(seed0)
+        p.set_wind_grid(gx, gy, gz, uvw, datum, spacing)
+        iG, jG = p.pattern()
+        x0 = p.x0()
+        rng = np.random.Generator(np.random.PCG64(seed0 + 1000))
+        X = [x0] + [perturb(x0, seed0 + s) for s in range(ns - 1)]
+        for s in range(3, ns):
+            X[s] = X[s].copy()
+            X[s][1:] += np.tile(np.r_[rng.uniform(-70, 70, 2), rng.uniform(-40, 40, 1), np.zeros(8)], p.ts + 1)
+        X = np.stack(X)
+        F, G = np.empty((ns, p.neF)), np.empty((ns, p.neG))
+        Wn = np.empty((ns, 12, p.ts + 1))
+        mask = p.ub_mask()
+        for s in range(ns):
+            F[s], G[s] = p.eval(X[s])
+            Wn[s] = p.wind()
+            G[s, mask] = 0.0
+        np.savez_compressed(
+            os.path.join(OUT, name + ".npz"), mission=mission, aircraft=ac, enu=np.array(enu, float),
+            goal_enu=np.array(goal, float), ts=p.ts, n=p.n, neF=p.neF, neG=p.neG, nb=p.nb,
+            ac=prm["ac"], gn=prm["gn"], lm=prm["lm"], sn=prm["sn"], goal_ned=prm["goal"], wind_model=3,
+            chi_d=p.chi_d(), iGfun=iG, jGvar=jG, ub_mask=mask, seed0=seed0, x=X, F=F, G=G, wind_nodes=Wn,
+            grid_x=gx, grid_y=gy, grid_z=gz, grid_v=np.ascontiguousarray(uvw[..., 1]), grid_datum=datum,
+            grid_spacing=spacing, **dict(zip(("xlow", "xupp", "Flow", "Fupp"), p.bounds())))
+        index[name] = dict(mission=mission, aircraft=ac, ts=p.ts, n=p.n, neF=p.neF, neG=p.neG, samples=ns,
+                           F0=float(F[0, 0]), wind_model=3)
+        print(name, p.n, p.neF, p.neG, "F[0]=%r" % F[0, 0])
+        p.close()
     for name, mission, ac, enu, goal, ts, gains, seed0, ns in CASES:
         p = R.RefProblem(mission, ac, enu, goal, ts=ts, gains=gains)
         prm = p.params()

@@ -16,7 +16,10 @@ class ToloProblem(C.Structure):
     _fields_ = [(k, C.c_int) for k in
                 ("formulation", "ts", "numinp", "numstates", "numbounds", "wind_model")] + \
                [(k, C.c_double) for k in
-                ("mm", "SS", "ee", "AR", "Cd0", "kT", "kp", "kv", "kdt", "xg", "yg", "rg", "chi_d")]
+                ("mm", "SS", "ee", "AR", "Cd0", "kT", "kp", "kv", "kdt", "xg", "yg", "rg", "chi_d")] + \
+               [(k, C.c_int) for k in ("grid_ne", "grid_nn", "grid_nu")] + \
+               [(k, C.POINTER(C.c_double)) for k in ("grid_x", "grid_y", "grid_z", "grid_v")] + \
+               [("datum", C.c_double * 3), ("spacing", C.c_double * 3)]
 
 
 _lib = None
@@ -61,9 +64,21 @@ class PortProblem:
         self.p = ToloProblem(form, int(ts), 11, 8, nb, int(wind_model), ac[0], ac[2], ac[3], ac[4],
                              ac[5], gn[0], gn[1], gn[2], gn[4], goal[0], goal[1], goal[3], chi_d)
         self.mission, self.ts, self.nb = mission, int(ts), nb
+        self._grid = None
         n, neF, neG = C.c_int(), C.c_int(), C.c_int()
         lib().tolo_dims(C.byref(self.p), C.byref(n), C.byref(neF), C.byref(neG))
         self.n, self.neF, self.neG = n.value, neF.value, neG.value
+
+    def set_wind_grid(self, gx, gy, gz, v, datum, spacing):
+        """wind model 3 on a wind cube: v[ne, nn, nu] (the reference interpolates the v component only)"""
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (gx, gy, gz, v)]
+        assert arrs[3].shape == (arrs[0].size, arrs[1].size, arrs[2].size)
+        self._grid = arrs  # keep alive
+        self.p.wind_model = 3
+        self.p.grid_ne, self.p.grid_nn, self.p.grid_nu = arrs[0].size, arrs[1].size, arrs[2].size
+        self.p.grid_x, self.p.grid_y, self.p.grid_z, self.p.grid_v = (_dp(a) for a in arrs)
+        self.p.datum[:] = [float(t) for t in datum]
+        self.p.spacing[:] = [float(t) for t in spacing]
 
     def pattern(self):
         i = np.empty(self.neG, np.int32)

@@ -60,8 +60,32 @@ struct ProbeG7 : problemG7 {
     using problem::yg;
     using problem::zg;
     using problem::rg;
-    using problem::Pwindmodel;
     using problemG7::chi_d;
+    using problem::Pwindmodel;
+    using problem::cache;
+    using problem::cache_east;
+    using problem::cache_north;
+    using problem::cache_up;
+    using problem::xspacing;
+    using problem::yspacing;
+    using problem::zspacing;
+    using problem::EastFromDatum;
+    using problem::NorthFromDatum;
+    using problem::UpFromDatum;
+    using problem::u;
+    using problem::v;
+    using problem::w;
+    using problem::du_dx;
+    using problem::du_dy;
+    using problem::du_dz;
+    using problem::dv_dx;
+    using problem::dv_dy;
+    using problem::dv_dz;
+    using problem::dw_dx;
+    using problem::dw_dy;
+    using problem::dw_dz;
+    typedef problem::winddoc wdoc;
+
 };
 struct ProbeS10 : problemS10 {
     explicit ProbeS10(arguments &a) : problemS10(a) {}
@@ -85,6 +109,29 @@ struct ProbeS10 : problemS10 {
     using problem::zg;
     using problem::rg;
     using problem::Pwindmodel;
+    using problem::cache;
+    using problem::cache_east;
+    using problem::cache_north;
+    using problem::cache_up;
+    using problem::xspacing;
+    using problem::yspacing;
+    using problem::zspacing;
+    using problem::EastFromDatum;
+    using problem::NorthFromDatum;
+    using problem::UpFromDatum;
+    using problem::u;
+    using problem::v;
+    using problem::w;
+    using problem::du_dx;
+    using problem::du_dy;
+    using problem::du_dz;
+    using problem::dv_dx;
+    using problem::dv_dy;
+    using problem::dv_dz;
+    using problem::dw_dx;
+    using problem::dw_dy;
+    using problem::dw_dz;
+    typedef problem::winddoc wdoc;
 };
 
 struct Handle {
@@ -99,6 +146,27 @@ struct CoutSilencer {
     CoutSilencer() : old(std::cout.rdbuf(sink.rdbuf())) {}
     ~CoutSilencer() { std::cout.rdbuf(old); }
 };
+
+
+template <class P>
+static void set_grid(P *p, int ne, int nn, int nu, const double *gx, const double *gy, const double *gz,
+                     const double *vals, const double *datum, const double *spacing) {
+    p->cache.clear();
+    for (int i = 0; i < ne; i++) {
+        p->cache.push_back(std::vector<std::vector<typename P::wdoc> >());
+        for (int j = 0; j < nn; j++) {
+            p->cache[i].push_back(std::vector<typename P::wdoc>());
+            for (int k = 0; k < nu; k++) {
+                const double *q = vals + 3 * ((size_t)(i * nn + j) * nu + k);
+                p->cache[i][j].push_back(typename P::wdoc(gx[i], gy[j], gz[k], q[0], q[1], q[2]));
+            }
+        }
+    }
+    p->cache_east = ne, p->cache_north = nn, p->cache_up = nu;
+    p->EastFromDatum = datum[0], p->NorthFromDatum = datum[1], p->UpFromDatum = datum[2];
+    p->xspacing = spacing[0], p->yspacing = spacing[1], p->zspacing = spacing[2];
+    p->Pwindmodel = 3;
+}
 
 }  // namespace
 
@@ -208,6 +276,29 @@ void tolref_params(void *hv, double *ac, double *gn, double *lm, double *sn, dou
     memcpy(sn, sv, sizeof sv);
     goal[0] = FIELD(h, xg), goal[1] = FIELD(h, yg), goal[2] = FIELD(h, zg), goal[3] = FIELD(h, rg);
     *wind_model = FIELD(h, Pwindmodel);
+}
+
+/* Wind model 3 of the reference (src/problem.cpp:544-695) without its MongoDB server: fill the protected
+ * wind cache the way cacheWind would (src/problem.cpp:443-459: cache[i][j][k], i < cache_east,
+ * j < cache_north, k < cache_up, each entry a winddoc x,y,z,u,v,w) and switch Pwindmodel to 3.  gx[i], gy[j],
+ * gz[k] are the grid coordinates (ENU, metres from the datum), vals = 3 values (u,v,w) per grid point in
+ * i-major order.  The reference code that consumes the cache runs unmodified. */
+void tolref_set_wind_grid(void *hv, int ne, int nn, int nu, const double *gx, const double *gy, const double *gz,
+                          const double *vals, const double *datum, const double *spacing) {
+    Handle *h = (Handle *)hv;
+    if (h->g7) set_grid(h->g7, ne, nn, nu, gx, gy, gz, vals, datum, spacing);
+    else set_grid(h->s10, ne, nn, nu, gx, gy, gz, vals, datum, spacing);
+}
+
+/* the 12 per-node wind arrays as the last modelWind call left them, out[12][ts+1] in member order
+ * u,v,w,du_dx,du_dy,du_dz,dv_dx,dv_dy,dv_dz,dw_dx,dw_dy,dw_dz (include/problem.h:103) */
+void tolref_get_wind(void *hv, double *out) {
+    Handle *h = (Handle *)hv;
+    const int nodes = FIELD(h, sn).ts + 1;
+#define CPW(i, f) memcpy(out + (size_t)(i) * nodes, FIELD(h, f).data(), sizeof(double) * nodes)
+    CPW(0, u); CPW(1, v); CPW(2, w); CPW(3, du_dx); CPW(4, du_dy); CPW(5, du_dz);
+    CPW(6, dv_dx); CPW(7, dv_dy); CPW(8, dv_dz); CPW(9, dw_dx); CPW(10, dw_dy); CPW(11, dw_dz);
+#undef CPW
 }
 
 double tolref_chi_d(void *hv) {

@@ -33,6 +33,8 @@ def lib():
         L.tolref_x0.argtypes = [C.c_void_p, dp]
         L.tolref_bounds.argtypes = [C.c_void_p, dp, dp, dp, dp]
         L.tolref_params.argtypes = [C.c_void_p, dp, dp, dp, dp, dp, ip]
+        L.tolref_set_wind_grid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp]
+        L.tolref_get_wind.argtypes = [C.c_void_p, dp]
         L.tolref_chi_d.restype = C.c_double
         L.tolref_chi_d.argtypes = [C.c_void_p]
         L.tolref_eval.argtypes = [C.c_void_p, dp, C.c_int, dp, C.c_int, dp]
@@ -127,6 +129,20 @@ class RefProblem:
         wm = C.c_int()
         lib().tolref_params(self.h, _dp(ac), _dp(gn), _dp(lm), _dp(sn), _dp(goal), C.byref(wm))
         return dict(ac=ac, gn=gn, lm=lm, sn=sn, goal=goal, wind_model=wm.value)
+
+    def set_wind_grid(self, gx, gy, gz, uvw, datum, spacing):
+        """switch the reference to its wind model 3 on a synthetic wind cube; uvw[ne, nn, nu, 3]"""
+        gx, gy, gz = (np.ascontiguousarray(a, dtype=np.float64) for a in (gx, gy, gz))
+        uvw = np.ascontiguousarray(uvw, dtype=np.float64)
+        assert uvw.shape == (gx.size, gy.size, gz.size, 3)
+        d, sp = np.asarray(datum, float), np.asarray(spacing, float)
+        lib().tolref_set_wind_grid(self.h, gx.size, gy.size, gz.size, _dp(gx), _dp(gy), _dp(gz), _dp(uvw),
+                                   _dp(d), _dp(sp))
+
+    def wind(self):
+        out = np.empty((12, self.ts + 1))
+        lib().tolref_get_wind(self.h, _dp(out))
+        return out
 
     def chi_d(self):
         return lib().tolref_chi_d(self.h)

@@ -41,8 +41,11 @@ def assert_parity(got, ref, what=""):
 
 def port_from_golden(g):
     import portclient as P
-    return P.PortProblem(str(g["mission"]), int(g["ts"]), g["ac"], g["gn"], g["goal_ned"],
-                         int(g["wind_model"]))
+    wm = int(g["wind_model"])
+    p = P.PortProblem(str(g["mission"]), int(g["ts"]), g["ac"], g["gn"], g["goal_ned"], 1 if wm == 3 else wm)
+    if wm == 3:
+        p.set_wind_grid(g["grid_x"], g["grid_y"], g["grid_z"], g["grid_v"], g["grid_datum"], g["grid_spacing"])
+    return p
 
 
 @pytest.fixture(scope="session")

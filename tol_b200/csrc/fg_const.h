@@ -38,6 +38,12 @@ struct FgConst {
     double xg, yg, rg;
     double cos_chid, sin_chid; // cos/sin of chi_d = atan2(yg - yi, xg - xi), src/problemG7.cpp:524
     double wind_Wxz;           // dWx_dz = -dv_dz = -(-Vref/href), src/problem.cpp:524,975
+    // wind model 3: the cached wind cube (device pointers), src/problem.cpp:443-459, 544-695
+    int grid_ne, grid_nn, grid_nu, pad2_;
+    const double *grid_x, *grid_y, *grid_z;  // cache[i][0][0].x, cache[0][j][0].y, cache[0][0][k].z
+    const double *grid_v;                    // cache[i][j][k].v, i-major
+    double datum[3];                         // EastFromDatum, NorthFromDatum, UpFromDatum
+    double spacing[3];                       // xspacing, yspacing, zspacing
 };
 
 #endif

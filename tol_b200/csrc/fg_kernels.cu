@@ -160,6 +160,77 @@ __device__ __forceinline__ void record_store(double *rec, const double *v, const
     st2(rec + 100, 0.0, mdt);
 }
 
+// ---- wind model 3: trilinear interpolation of the cached wind cube, src/problem.cpp:544-695 -------------
+//
+// Only the v component is interpolated by the reference (u, w and their gradients stay zero).  The cell
+// search keeps the reference's comparisons (first index with coordinate - grid < spacing; sic: the x search
+// is bounded by the cube's second dimension and the y search by its first); where the reference would then
+// index past the cube (undefined behaviour) the last cell is used instead.
+__device__ __forceinline__ void wind_cube(const FgConst &c, const double xn, const double yn, const double zn,
+                                          double &v, double &dv_dx, double &dv_dy, double &dv_dz) {
+    const double xs = yn + c.datum[0];  // ENU <- NED, :551-553
+    const double ys = xn + c.datum[1];
+    const double zs = -zn + c.datum[2];
+    const double dx = c.spacing[0], dy = c.spacing[1], dz = c.spacing[2];
+    int xi, yi, zi;
+    for (xi = 0; xi < c.grid_nn; xi++)
+        if ((xs - __ldg(c.grid_x + xi)) < dx) break;
+    for (yi = 0; yi < c.grid_ne; yi++)
+        if ((ys - __ldg(c.grid_y + yi)) < dy) break;
+    for (zi = 0; zi < c.grid_nu; zi++)
+        if ((zs - __ldg(c.grid_z + zi)) < dz) break;
+    xi = min(xi, c.grid_ne - 2), yi = min(yi, c.grid_nn - 2), zi = min(zi, c.grid_nu - 2);
+    const double *g0 = c.grid_v + ((size_t)xi * c.grid_nn + yi) * c.grid_nu + zi;
+    const size_t sx = (size_t)c.grid_nn * c.grid_nu, sy = c.grid_nu;
+    double vc[8];
+    vc[0] = __ldg(g0), vc[1] = __ldg(g0 + sx), vc[2] = __ldg(g0 + sy), vc[3] = __ldg(g0 + sx + sy);
+    vc[4] = __ldg(g0 + 1), vc[5] = __ldg(g0 + sx + 1), vc[6] = __ldg(g0 + sy + 1), vc[7] = __ldg(g0 + sx + sy + 1);
+    const double xrel = (xs - __ldg(c.grid_x + xi)), yrel = (ys - __ldg(c.grid_y + yi)), zrel = (zs - __ldg(c.grid_z + zi));
+    const double zeta = xrel / dx, eta = yrel / dy, mu = zrel / dz;
+    const double dxdy = dx * dy, dxdz = dx * dz, dydz = dy * dz, dxdydz = dx * dy * dz;
+    double N[8], NX[8], NY[8], NZ[8];
+    N[0] = (1 - zeta) * (1 - eta) * (1 - mu);  // :618-625
+    N[1] = zeta * (1 - eta) * (1 - mu);
+    N[2] = (1 - zeta) * eta * (1 - mu);
+    N[3] = zeta * eta * (1 - mu);
+    N[4] = (1 - zeta) * (1 - eta) * mu;
+    N[5] = zeta * (1 - eta) * mu;
+    N[6] = (1 - zeta) * eta * mu;
+    N[7] = zeta * eta * mu;
+    NX[0] = -((eta - 1.0) * (mu - 1.0)) / dx;  // :643-650 (yrel/dy == eta, zrel/dz == mu)
+    NX[1] = ((eta - 1.0) * (mu - 1.0)) / dx;
+    NX[2] = (yrel * (mu - 1.0)) / dxdy;
+    NX[3] = -(yrel * (mu - 1.0)) / dxdy;
+    NX[4] = (zrel * (eta - 1.0)) / dxdz;
+    NX[5] = -(zrel * (eta - 1.0)) / dxdz;
+    NX[6] = -(yrel * zrel) / dxdydz;
+    NX[7] = (yrel * zrel) / dxdydz;
+    NY[0] = -((zeta - 1.0) * (mu - 1.0)) / dy;  // :653-660
+    NY[1] = (xrel * (mu - 1.0)) / dxdy;
+    NY[2] = ((zeta - 1.0) * (mu - 1.0)) / dy;
+    NY[3] = -(xrel * (mu - 1.0)) / dxdy;
+    NY[4] = (zrel * (zeta - 1.0)) / dydz;
+    NY[5] = -(xrel * zrel) / dxdydz;
+    NY[6] = -(zrel * (zeta - 1.0)) / dydz;
+    NY[7] = (xrel * zrel) / dxdydz;
+    NZ[0] = -((zeta - 1.0) * (eta - 1.0)) / dz;  // :663-670
+    NZ[1] = (xrel * (eta - 1.0)) / dxdz;
+    NZ[2] = (yrel * (zeta - 1.0)) / dydz;
+    NZ[3] = -(xrel * yrel) / dxdydz;
+    NZ[4] = ((zeta - 1.0) * (eta - 1.0)) / dz;
+    NZ[5] = -(xrel * (eta - 1.0)) / dxdz;
+    NZ[6] = -(yrel * (zeta - 1.0)) / dydz;
+    NZ[7] = (xrel * yrel) / dxdydz;
+    v = 0.0, dv_dx = 0.0, dv_dy = 0.0, dv_dz = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {  // :631-635, :682-692
+        v += N[i] * vc[i];
+        dv_dx += NX[i] * vc[i];
+        dv_dy += NY[i] * vc[i];
+        dv_dz += NZ[i] * vc[i];
+    }
+}
+
 // ---- one warp, one tile of 32 windows ---------------------------------------------------------------
 //
 // sx: the warp's staged x slice (slot 0 = x[11*k0], node j of the slice at sx[1+11j]).  Once every lane
@@ -172,7 +243,8 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
                                           const int k0, const int nk, const int lane,
                                           double *__restrict__ Fb, double *__restrict__ Gb,
                                           const int needF, const int needG, double &sumT, double &sump) {
-    constexpr bool W = (WIND == 1);
+    constexpr bool X3 = (WIND == 3);             // wind cube: Wx with all three gradient components
+    constexpr bool W = (WIND == 1) || X3;        // Wx and dWx/dz present
     constexpr bool S10 = (FORM == TOLCUDA_FORM_S10);
     const int ts = c.ts;
     const int k = k0 + lane;
@@ -192,13 +264,20 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
         sincos(gam, &sg, &cg);
         sincos(phi, &sp, &cp);
     }
-    // wind, NED <- ENU (src/problem.cpp:522-524, 970-981): Wx = v = -Vref*zs/href with zs = -z,
-    // dWx_dz = -dv_dz; every other component is exactly zero under models 0 and 1
-    const double Wxz = c.wind_Wxz;
+    // wind, NED <- ENU (src/problem.cpp:970-981): Wx = v, dWx_dx = dv_dy, dWx_dy = dv_dx, dWx_dz = -dv_dz;
+    // every other component is exactly zero under models 0, 1 and 3.
+    //   model 1 (:522-524): v = -Vref*zs/href with zs = -z, dv_dz = -Vref/href
+    //   model 3 (:544-695): v and its gradient interpolated from the wind cube (wind_cube)
+    double Wxz = c.wind_Wxz, Wxx = 0.0, Wxy = 0.0;
     double Wx = 0.0;
-    if (W) {
+    if (WIND == 1) {
         const double zs = -z;
         Wx = -2.4 * zs / 10.0;
+    }
+    if (X3) {
+        double dv_dx, dv_dy, dv_dz;
+        wind_cube(c, s0[0], s0[1], z, Wx, dv_dx, dv_dy, dv_dz);
+        Wxx = dv_dy, Wxy = dv_dx, Wxz = -dv_dz;
     }
     // (Wx + Va*cos(chi)*cos(gam)), (Wy + Va*cos(gam)*sin(chi)), (Wz - Va*sin(gam))
     const double Vacc = Va * cc, Vacg = Va * cg, Vasg = Va * sg;
@@ -216,6 +295,20 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
         ez = -((Wxz * cg) * sc);  // (dWy_dz*cc*cg - dWx_dz*cg*sc)
         fz = -(Wxzsc * sg);       // (dWy_dz*cc*sg - dWx_dz*sc*sg)
     }
+    // the x- and y-column instances of the same brackets (wind cube only)
+    double ax = 0, ay = 0, bx = 0, by = 0, cx = 0, cy = 0, dxw = 0, dyw = 0, ex = 0, ey = 0, fx = 0, fy = 0;
+    if (X3) {
+        const double Wxxcc = Wxx * cc, Wxycc = Wxy * cc, Wxxsc = Wxx * sc, Wxysc = Wxy * sc;
+        ax = Wxxcc * cg, ay = Wxycc * cg;
+        bx = Wxxcc * sg, by = Wxycc * sg;
+        cx = -Wxxsc, cy = -Wxysc;
+        dxw = Wxxcc, dyw = Wxycc;
+        ex = -((Wxx * cg) * sc), ey = -((Wxy * cg) * sc);
+        fx = -(Wxxsc * sg), fy = -(Wxysc * sg);
+    }
+    const double ccg = cc * cg, cgsc = cg * sc;                  // cos(chi)*cos(gam), cos(gam)*sin(chi)
+    const double Vaccsg = Vacc * sg, Vascsg = Va * sc * sg;       // Va*cos(chi)*sin(gam), Va*sin(chi)*sin(gam)
+    const double Vacccg = Vacc * cg;                              // Va*cos(chi)*cos(gam)
     const double rVa = 1.0 / Va, rVacg = 1.0 / Vacg;
     const double CdT = c.Cd0 + div_r(CL * CL, c.ARpiee, c.r_ARpiee);  // (Cd0 + CL*CL/(AR*pi*ee))
     const double rSV = c.rhoSS * Va;                                  // rho*SS*Va
@@ -224,7 +317,11 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
     const double Va2 = Va * Va;
     const double Tmm = div_r(T, c.mm, c.r_mm);
     const double gsg = c.g * sg, gcg = c.g * cg;
-    const double n4 = W ? vz * bz - gcg : -gcg;  // (vx*bx + vy*by + vz*bz - g*cos(gam))
+    // (vx*bx + vy*by + vz*bz - g*cos(gam))
+    const double n4 = X3 ? vx * bx + vy * by + vz * bz - gcg : (W ? vz * bz - gcg : -gcg);
+    // (vx*ax + vy*ay + vz*az) and (vz*cz + cx*vx + vy*cy)
+    const double va3 = X3 ? vx * ax + vy * ay + vz * az : vz * az;
+    const double vc3 = X3 ? vz * cz + cx * vx + vy * cy : vz * cz;
     const double Vadt = Va * dt, mdt = -dt;
 
     // ---- objective terms: src/problemS10.cpp:246-258, 340-372; src/problemG7.cpp:240-241, 370 ----
@@ -258,10 +355,11 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
     double f[PF];
     {
         const double drag3 = div_r(rSV * Va * CdT, c.twomm, c.r_twomm);
-        const double dx3 = W ? Tmm - vz * az - gsg - drag3 : Tmm - gsg - drag3;
+        const double dx3 = X3 ? Tmm - vy * ay - vz * az - vx * ax - gsg - drag3
+                              : (W ? Tmm - vz * az - gsg - drag3 : Tmm - gsg - drag3);
         const double dx4 = div_r(n4 + div_r(CLrSV * Va * cp, c.twomm, c.r_twomm), Va, rVa);
         const double lift5 = div_r(CLrSV * Va * sp, c.twomm, c.r_twomm);
-        const double dx5 = W ? div_r(-(vz * cz - lift5), Vacg, rVacg) : div_r(-(-lift5), Vacg, rVacg);
+        const double dx5 = W ? div_r(-(vc3 - lift5), Vacg, rVacg) : div_r(-(-lift5), Vacg, rVacg);
         f[0] = s1[0] - vx * dt - s0[0];
         f[1] = s1[1] - vy * dt - s0[1];
         f[2] = s1[2] - vz * dt - s0[2];
@@ -328,10 +426,11 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
     {  // F4 :1125-1130
         const double dragv = div_r(rSV * CdT, c.mm, c.r_mm);
         const double drag11 = div_r(c.rhoSS * Va2 * CdT, c.twomm, c.r_twomm);
-        v[11] = W ? vz * az - Tmm + gsg + drag11 : -Tmm + gsg + drag11;
-        v[12] = W ? dt * (-(sg * az) + dragv) - 1.0 : dt * dragv - 1.0;
-        v[13] = W ? mdt * (n4 + Vacg * az) : mdt * n4;
-        v[14] = W ? dt * (ez * vz) : 0.0;
+        v[11] = W ? va3 - Tmm + gsg + drag11 : -Tmm + gsg + drag11;
+        v[12] = X3 ? dt * (ccg * ax - sg * az + cgsc * ay + dragv) - 1.0
+                   : (W ? dt * (-(sg * az) + dragv) - 1.0 : dt * dragv - 1.0);
+        v[13] = X3 ? mdt * (n4 + Vacg * az + Vaccsg * ax + Vascsg * ay) : (W ? mdt * (n4 + Vacg * az) : mdt * n4);
+        v[14] = X3 ? dt * (ex * vx + vy * ey + ez * vz + Vacccg * ay - vy * ax) : (W ? dt * (ez * vz) : 0.0);
         v[15] = div_r(CLrS * Va2 * dt, c.ARpieemm, c.r_ARpieemm);
         v[16] = div_r(mdt, c.mm, c.r_mm);
     }
@@ -340,25 +439,31 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
         const double S5 = n4 + div_r(CLrS * Va2 * cp, c.twomm, c.r_twomm);
         const double liftv = div_r(CLrSV * cp, c.mm, c.r_mm);
         v[17] = div_r(-S5, Va, rVa);
-        v[18] = W ? div_r(dt * S5, Va2, rVa2) - div_r(dt * (-(sg * bz) + liftv), Va, rVa)
+        v[18] = X3 ? div_r(dt * S5, Va2, rVa2) - div_r(dt * (ccg * bx - sg * bz + cgsc * by + liftv), Va, rVa)
+                : W ? div_r(dt * S5, Va2, rVa2) - div_r(dt * (-(sg * bz) + liftv), Va, rVa)
                   : div_r(dt * S5, Va2, rVa2) - div_r(dt * liftv, Va, rVa);
-        v[19] = W ? div_r(-(dt * (vz * az + gsg - Vacg * bz)), Va, rVa) - 1.0 : div_r(-(dt * gsg), Va, rVa) - 1.0;
-        v[20] = W ? div_r(-(dt * (fz * vz)), Va, rVa) : 0.0;
+        v[19] = X3 ? div_r(-(dt * (va3 + gsg - Vacg * bz - Vaccsg * bx - Vascsg * by)), Va, rVa) - 1.0
+                : W ? div_r(-(dt * (va3 + gsg - Vacg * bz)), Va, rVa) - 1.0 : div_r(-(dt * gsg), Va, rVa) - 1.0;
+        v[20] = X3 ? div_r(-(dt * (fx * vx + vy * fy + fz * vz + Vacccg * by - vy * bx)), Va, rVa)
+                : W ? div_r(-(dt * (fz * vz)), Va, rVa) : 0.0;
         v[21] = div_r(CLrSV * dt * sp, c.twomm, c.r_twomm);
         v[22] = div_r(-(rSV * dt * cp), c.twomm, c.r_twomm);
     }
     {  // F6 :1155-1160
         const double lift6 = div_r(CLrS * Va2 * sp, c.twomm, c.r_twomm);
-        const double Q = W ? vz * cz - lift6 : -lift6;
+        const double Q = W ? vc3 - lift6 : -lift6;
         const double sidev = div_r(CLrSV * sp, c.mm, c.r_mm);
         const double Va2cg = Va2 * cg, Vacg2 = Va * (cg * cg), tmcg = c.twomm * cg;
         const double rVa2cg = 1.0 / Va2cg, rVacg2 = 1.0 / Vacg2, rtmcg = 1.0 / tmcg;
         v[23] = div_r(Q, Vacg, rVacg);
-        v[24] = W ? div_r(-(dt * (sg * cz + sidev)), Vacg, rVacg) - div_r(dt * Q, Va2cg, rVa2cg)
+        v[24] = X3 ? div_r(-(dt * (sg * cz - ccg * cx - cgsc * cy + sidev)), Vacg, rVacg) - div_r(dt * Q, Va2cg, rVa2cg)
+                : W ? div_r(-(dt * (sg * cz + sidev)), Vacg, rVacg) - div_r(dt * Q, Va2cg, rVa2cg)
                   : div_r(-(dt * sidev), Vacg, rVacg) - div_r(dt * Q, Va2cg, rVa2cg);
-        v[25] = W ? div_r(dt * sg * Q, Vacg2, rVacg2) - div_r(dt * (Vacg * cz), Vacg, rVacg)
+        v[25] = X3 ? div_r(dt * sg * Q, Vacg2, rVacg2) - div_r(dt * (Vacg * cz + Vaccsg * cx + Vascsg * cy), Vacg, rVacg)
+                : W ? div_r(dt * sg * Q, Vacg2, rVacg2) - div_r(dt * (Vacg * cz), Vacg, rVacg)
                   : div_r(dt * sg * Q, Vacg2, rVacg2);
-        v[26] = W ? div_r(-(dt * (vz * dz)), Vacg, rVacg) - 1.0 : -1.0;
+        v[26] = X3 ? div_r(-(dt * (vz * dz + dxw * vx + vy * dyw - Vacccg * cy + vy * cx)), Vacg, rVacg) - 1.0
+                : W ? div_r(-(dt * (vz * dz)), Vacg, rVacg) - 1.0 : -1.0;
         v[27] = div_r(-(CLrSV * dt * cp), tmcg, rtmcg);
         v[28] = div_r(-(rSV * dt * sp), tmcg, rtmcg);
     }
@@ -666,9 +771,11 @@ cudaError_t fg_launch(const FgLaunch &L) {
     if (L.c->form == TOLCUDA_FORM_S10) {
         if (L.c->wind == 1) return launch_any<TOLCUDA_FORM_S10, 1>(L);
         if (L.c->wind == 0) return launch_any<TOLCUDA_FORM_S10, 0>(L);
+        if (L.c->wind == 3) return launch_any<TOLCUDA_FORM_S10, 3>(L);
     } else if (L.c->form == TOLCUDA_FORM_G7) {
         if (L.c->wind == 1) return launch_any<TOLCUDA_FORM_G7, 1>(L);
         if (L.c->wind == 0) return launch_any<TOLCUDA_FORM_G7, 0>(L);
+        if (L.c->wind == 3) return launch_any<TOLCUDA_FORM_G7, 3>(L);
     }
     return cudaErrorInvalidValue;
 }

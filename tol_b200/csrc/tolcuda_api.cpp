@@ -58,6 +58,7 @@ struct tolcuda_ctx {
     // host-pointer batch path
     BatchLane lane[2];
     long launches = 0;
+    double *d_grid = nullptr;  // wind cube: gx | gy | gz | v
 };
 
 namespace {
@@ -271,6 +272,32 @@ int tolcuda_create_from_files(const char *root, const char *aircraft, const char
     return tolcuda_create(&cfg, out);
 }
 
+int tolcuda_set_wind_grid(tolcuda_handle h, int ne, int nn, int nu, const double *gx, const double *gy,
+                          const double *gz, const double *v, const double *datum, const double *spacing) {
+    if (!h || ne < 2 || nn < 2 || nu < 2 || !gx || !gy || !gz || !v || !datum || !spacing) {
+        set_error("tolcuda_set_wind_grid: need at least 2 grid points per axis and non-null arrays");
+        return TOLCUDA_EINVAL;
+    }
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->d_grid) CU(cudaFree(h->d_grid));
+    h->d_grid = nullptr;
+    const size_t nv = (size_t)ne * nn * nu, tot = (size_t)ne + nn + nu + nv;
+    CU(cudaMalloc(&h->d_grid, sizeof(double) * tot));
+    double *d = h->d_grid;
+    CU(cudaMemcpy(d, gx, sizeof(double) * ne, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d + ne, gy, sizeof(double) * nn, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d + ne + nn, gz, sizeof(double) * nu, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d + ne + nn + nu, v, sizeof(double) * nv, cudaMemcpyHostToDevice));
+    FgConst &c = h->c;
+    c.grid_ne = ne, c.grid_nn = nn, c.grid_nu = nu;
+    c.grid_x = d, c.grid_y = d + ne, c.grid_z = d + ne + nn, c.grid_v = d + ne + nn + nu;
+    for (int i = 0; i < 3; i++) c.datum[i] = datum[i], c.spacing[i] = spacing[i];
+    c.wind = TOLCUDA_WIND_CUBE;
+    h->cfg.wind_model = TOLCUDA_WIND_CUBE;
+    return 0;
+}
+
 int tolcuda_destroy(tolcuda_handle h) {
     if (!h) return 0;
     {
@@ -283,6 +310,7 @@ int tolcuda_destroy(tolcuda_handle h) {
     free_lane(h->lane[1]);
     if (h->h_one) cudaFreeHost(h->h_one);
     if (h->d_one) cudaFree(h->d_one);
+    if (h->d_grid) cudaFree(h->d_grid);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return 0;

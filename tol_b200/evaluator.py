@@ -97,7 +97,10 @@ class Evaluator:
     def from_golden(cls, g, device=0, wind_model=None):
         """g: an opened tests/golden/*.npz fixture"""
         wm = int(g["wind_model"]) if wind_model is None else wind_model
-        return cls(str(g["mission"]), int(g["ts"]), g["ac"], g["gn"], g["goal_ned"], wm, device)
+        ev = cls(str(g["mission"]), int(g["ts"]), g["ac"], g["gn"], g["goal_ned"], 1 if wm == 3 else wm, device)
+        if wm == 3:
+            ev.set_wind_grid(g["grid_x"], g["grid_y"], g["grid_z"], g["grid_v"], g["grid_datum"], g["grid_spacing"])
+        return ev
 
     def _finish(self, L, device):
         self.L, self.device = L, device
@@ -111,6 +114,12 @@ class Evaluator:
             self.h = None
 
     __del__ = close
+
+    def set_wind_grid(self, gx, gy, gz, v, datum, spacing):
+        """tolcuda_set_wind_grid: reference wind model 3 on a wind cube v[ne, nn, nu]"""
+        a = [np.ascontiguousarray(t, dtype=np.float64) for t in (gx, gy, gz, v, datum, spacing)]
+        assert a[3].shape == (a[0].size, a[1].size, a[2].size)
+        _l.check(self.L.tolcuda_set_wind_grid(self.h, a[0].size, a[1].size, a[2].size, *[_dp(t) for t in a]))
 
     def pattern(self):
         i, j = np.empty(self.neG, np.int32), np.empty(self.neG, np.int32)

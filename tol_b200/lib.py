@@ -36,6 +36,7 @@ def load():
     L.tolcuda_create_from_files.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p] + [C.c_double] * 7 + \
         [C.c_int, C.c_int, C.POINTER(vp)]
     L.tolcuda_destroy.argtypes = [vp]
+    L.tolcuda_set_wind_grid.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp]
     L.tolcuda_dims.argtypes = [vp, ip, ip, ip]
     L.tolcuda_pattern.argtypes = [vp, ip, ip]
     L.tolcuda_problem_dims.argtypes = [C.c_int, C.c_int, ip, ip, ip]
