@@ -133,6 +133,17 @@ int tolcuda_eval(tolcuda_handle h, const double *x, int needF, double *F, int ne
 int tolcuda_eval_batch(tolcuda_handle h, int B, const double *x, long ldx, double *F, long ldF,
                        double *G, long ldG, int flags);
 
+/* Same evaluation plus a per-trajectory summary computed inside the kernel from values it already holds
+ * (a device-side consumer of F; nothing of the kind exists in the reference, where SNOPT alone reads F):
+ *   summary[b*lds + 0] = F[0]                      objective
+ *   summary[b*lds + 1] = max |defect|              over the 8*ts dynamics rows
+ *   summary[b*lds + 2] = max boundary violation    |row| for equality rows, max(row, 0) for G7's dist <= dmax
+ *   summary[b*lds + 3] = sum of defect^2
+ * lds >= 4; same pointer kind as x/F/G.  With neither TOLCUDA_NEED_F nor TOLCUDA_NEED_G only the summary
+ * is produced (F and G may then be NULL). */
+int tolcuda_eval_batch_summary(tolcuda_handle h, int B, const double *x, long ldx, double *F, long ldF,
+                               double *G, long ldG, double *summary, long lds, int flags);
+
 /* page-locked host memory for x/F/G of the host-pointer batch path (full PCIe speed, asynchronous
  * copies); plain wrappers so that a C/C++ driver needs no CUDA headers */
 int tolcuda_host_alloc(size_t bytes, void **ptr);

@@ -286,3 +286,32 @@ def test_defect_cancellation_at_the_exact_initial_guess(oracle_built):
     d = slice(1, 1 + 8 * ts)
     assert (err[d] <= 1e-14 + 1e-12 * np.abs(Fr[d]) + np.spacing(scale)).all()
     assert_parity(np.delete(F, np.arange(1, 1 + 8 * ts)), np.delete(Fr, np.arange(1, 1 + 8 * ts)), "F[0], boundary")
+
+
+@pytest.mark.parametrize("name", ["S10_tempest_ts100", "G7_skywalker_ts100", "G7_tempestwences_ts45_gains",
+                                  "S10_tempest_ts100_wind3"])
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_fused_trajectory_summary(name, kernel, monkeypatch):
+    """tolcuda_eval_batch_summary: objective / max|defect| / max boundary violation / sum defect^2 computed
+    in the kernel equal the same quantities computed on the host from the kernel's own F (max: exactly;
+    sum of squares: to rounding), with and without F/G being written"""
+    monkeypatch.setenv("TOLCUDA_KERNEL", str(kernel))
+    g = load_golden(name)
+    ev = T.Evaluator.from_golden(g)
+    B = 33
+    X = T.synth.batch(g["x"][0], 909, 0, B)
+    S, F, G = ev.summary_host(X, needF=True, needG=True)
+    S2, _, _ = ev.summary_host(X)
+    assert np.array_equal(S, S2)
+    ts, nb = int(g["ts"]), int(g["nb"])
+    d = F[:, 1:1 + 8 * ts]
+    bnd = np.abs(F[:, -nb:])
+    if str(g["mission"]) == "G7":
+        bnd[:, -1] = np.maximum(F[:, -1], 0.0)
+    assert np.array_equal(S[:, 0], F[:, 0])
+    assert np.array_equal(S[:, 1], np.abs(d).max(axis=1))
+    assert np.array_equal(S[:, 2], bnd.max(axis=1))
+    assert np.allclose(S[:, 3], (d * d).sum(axis=1), rtol=1e-13, atol=0)
+    Fr, Gr = ev.eval_batch_host(X)
+    assert np.array_equal(F, Fr) and np.array_equal(G, Gr)
+    ev.close()

@@ -57,6 +57,18 @@ constexpr int WARP_SMEM_B = 2 * SX_LEN + TILE_LEN;  // kernel B: double-buffered
 constexpr int F_LD = 10;               // smem stride of a window's 8 defects (== 2 mod 4)
 constexpr int NVAR = 31;               // x-dependent entries of a record (plus two -dt entries)
 
+// per-lane partial results a tile hands back: cost sums and the feasibility summary of its defects
+struct TileSums {
+    double sumT, sump;  // sum of T^2, sum of (r-R)^2 (S10)
+    double dmax, dssq;  // max |defect|, sum of defect^2 (SUMM instantiations only)
+};
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, m));
+    return v;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
@@ -238,11 +250,12 @@ __device__ __forceinline__ void wind_cube(const FgConst &c, const double xn, con
 // tile: the warp's NBUF x NPP record slots, constants already in place (record_init).
 // needG carries two experiment switches in bits 2 and 3 (tools/kbench.py): 4 = stage but do not store
 // G, 8 = no trigonometry.
-template <int FORM, int WIND>
+template <int FORM, int WIND, bool SUMM>
 __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *tile, const double dt,
                                           const int k0, const int nk, const int lane,
                                           double *__restrict__ Fb, double *__restrict__ Gb,
-                                          const int needF, const int needG, double &sumT, double &sump) {
+                                          const int needF, const int needG, TileSums &ts_out) {
+    double &sumT = ts_out.sumT, &sump = ts_out.sump;
     constexpr bool X3 = (WIND == 3);             // wind cube: Wx with all three gradient components
     constexpr bool W = (WIND == 1) || X3;        // Wx and dWx/dz present
     constexpr bool S10 = (FORM == TOLCUDA_FORM_S10);
@@ -368,6 +381,18 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
         f[5] = s1[5] - dx5 * dt - s0[5];
         f[6] = s1[6] - dphi * dt - s0[6];
         f[7] = s1[7] - dCL * dt - s0[7];
+    }
+    ts_out.dmax = 0.0, ts_out.dssq = 0.0;
+    if (SUMM) {
+        double m = 0.0, q = 0.0;
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < PF; i++) {
+                m = fmax(m, fabs(f[i]));
+                q += f[i] * f[i];
+            }
+        }
+        ts_out.dmax = m, ts_out.dssq = q;
     }
     __syncwarp();  // every lane has read its window: the slice is dead, sx becomes the staging area
 
@@ -508,12 +533,12 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
 
 // Out-of-line instance for the persistent kernel: inlined into its trajectory/tile loop, ptxas keeps
 // dozens of extra values live across the loop and spills; as a call the tile body is allocated on its own.
-template <int FORM, int WIND>
+template <int FORM, int WIND, bool SUMM>
 __device__ __noinline__ void tile_eval_call(const FgConst &c, double *sx, double *tile, const double dt,
                                             const int k0, const int nk, const int lane,
                                             double *__restrict__ Fb, double *__restrict__ Gb,
-                                            const int needF, const int needG, double &sumT, double &sump) {
-    tile_eval<FORM, WIND>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, sumT, sump);
+                                            const int needF, const int needG, TileSums &ts_out) {
+    tile_eval<FORM, WIND, SUMM>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, ts_out);
 }
 
 // ---- end of a trajectory: F[0], boundary rows, objective-row ends --------------------------------------
@@ -524,9 +549,11 @@ template <int FORM>
 __device__ __forceinline__ void traj_epilogue(const FgConst &c, const int lane, const double dt,
                                               const double tT, const double tp, const double n0,
                                               const double ne, double *__restrict__ Fb,
-                                              double *__restrict__ Gb, const int needF, const int needG) {
+                                              double *__restrict__ Gb, const int needF, const int needG,
+                                              const double dmax, const double dssq, double *__restrict__ Sb) {
     constexpr bool S10 = (FORM == TOLCUDA_FORM_S10);
     const int ts = c.ts;
+    double f0 = 0.0, bval = 0.0;  // objective (lane 0) and this lane's boundary-row value
     double *Fbnd = Fb + (c.neF - c.nb);
     double *Gbnd = Gb + c.R0 + (size_t)REC * ts;
     if (S10) {
@@ -537,6 +564,10 @@ __device__ __forceinline__ void traj_epilogue(const FgConst &c, const int lane, 
                 if (lane == 5) d = d - 2.0 * M_PI;
                 Fbnd[lane] = d;
             }
+        }
+        if (Sb) {
+            f0 = c.half_kT * tT + c.half_kp * tp + c.kdt * dt;
+            if (lane < PX) bval = lane == 5 ? ne - n0 - 2.0 * M_PI : ne - n0;
         }
         if (needG) {
             if (lane == 0) Gb[0] = c.kdt;  // src/problemS10.cpp:378-381
@@ -562,6 +593,14 @@ __device__ __forceinline__ void traj_epilogue(const FgConst &c, const int lane, 
                 Fbnd[11] = dist - dmax;
             }
             if (lane >= 2 && lane < PX) Fbnd[lane] = ne - n0;
+        }
+        if (Sb) {
+            const double gx = c.xg - x0, gy = c.yg - y0;
+            f0 = c.half_kT * tT + c.kv_ts * dt / dist;
+            if (lane >= 2 && lane < PX) bval = ne - n0;
+            if (lane == 0) bval = ddx - dist * c.cos_chid;
+            if (lane == 1) bval = ddy - dist * c.sin_chid;
+            if (lane == PX) bval = fmax(dist - sqrt(gx * gx + gy * gy), 0.0);  // dist <= dmax: only excess counts
         }
         if (needG && lane == 0) {
             // objective row ends, src/problemG7.cpp:343-380 (sic: kp, where cost() uses kv)
@@ -589,6 +628,15 @@ __device__ __forceinline__ void traj_epilogue(const FgConst &c, const int lane, 
             p[0] = 0.0, p[1] = -ex, p[2] = -ey, p[3] = ex, p[4] = ey;
         }
     }
+    if (Sb) {  // [objective, max |defect|, max |boundary violation|, sum of defect^2]
+        const double bmax = warp_max(fabs(bval));
+        if (lane == 0) {
+            Sb[0] = f0;
+            Sb[1] = dmax;
+            Sb[2] = bmax;
+            Sb[3] = dssq;
+        }
+    }
 }
 
 // ---- kernel A: one CTA per trajectory ------------------------------------------------------------------
@@ -596,12 +644,13 @@ __device__ __forceinline__ void traj_epilogue(const FgConst &c, const int lane, 
 // grid.x = B, blockDim.x = 32*ceil(ts/32) (<= MAXT).  Warp w owns windows 32w..32w+31 and runs on its
 // own after start-up; the cost sum crosses warps through shared memory and an arrival counter, and the
 // last warp to arrive runs the trajectory epilogue.
-template <int FORM, int WIND, int MAXT, int MINB>
+template <int FORM, int WIND, int MAXT, int MINB, bool SUMM>
 __global__ void __launch_bounds__(MAXT, MINB)
 fg_cta_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, long ldx,
-              double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG) {
+              double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG,
+              double *__restrict__ S, long ldS) {
     extern __shared__ __align__(16) double smem[];
-    __shared__ double red[2][32];
+    __shared__ double red[SUMM ? 4 : 2][32];
     __shared__ int arrivals;
     const int ts = c.ts;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -629,16 +678,21 @@ fg_cta_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, l
     cp_async_wait<0>();
     __syncwarp();
 
-    double sumT, sump;
-    tile_eval<FORM, WIND>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, sumT, sump);
+    TileSums tsum;
+    tile_eval<FORM, WIND, SUMM>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, tsum);
 
     // cost sums: warp shuffle, then across warps through shared memory
-    sumT = warp_sum(sumT);
-    if (FORM == TOLCUDA_FORM_S10) sump = warp_sum(sump);
+    const double sumT = warp_sum(tsum.sumT);
+    const double sump = FORM == TOLCUDA_FORM_S10 ? warp_sum(tsum.sump) : 0.0;
+    const double wdmax = SUMM ? warp_max(tsum.dmax) : 0.0, wdssq = SUMM ? warp_sum(tsum.dssq) : 0.0;
     int last = 0;
     if (lane == 0) {
         red[0][warp] = sumT;
         red[1][warp] = sump;
+        if (SUMM) {
+            red[SUMM ? 2 : 0][warp] = wdmax;
+            red[SUMM ? 3 : 0][warp] = wdssq;
+        }
         __threadfence_block();
         last = (atomicAdd(&arrivals, 1) == nwarps - 1);
     }
@@ -646,12 +700,16 @@ fg_cta_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, l
     if (!last) return;
     __threadfence_block();
     const volatile double *vred = &red[0][0];
-    double tT = 0.0, tp = 0.0;
+    double tT = 0.0, tp = 0.0, dmax = 0.0, dssq = 0.0;
     for (int w = 0; w < nwarps; w++) {  // fixed order: deterministic
         tT += vred[w];
         tp += vred[32 + w];
+        if (SUMM) {
+            dmax = fmax(dmax, vred[64 + w]);
+            dssq += vred[96 + w];
+        }
     }
-    traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG);
+    traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG, dmax, dssq, SUMM ? S + b * ldS : nullptr);
 }
 
 // ---- kernel B: persistent warps, one trajectory per warp at a time ------------------------------------------
@@ -660,10 +718,11 @@ fg_cta_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, l
 // tiles in order, so cost sums stay in registers and no warp ever waits for another.  While a tile is
 // evaluated, the x slice of the next tile (or of the next trajectory's first tile) is already in flight
 // (cp.async) into the other slice buffer.  Selectable variant (TOLCUDA_KERNEL=2).
-template <int FORM, int WIND, int WARPS, int MINB>
+template <int FORM, int WIND, int WARPS, int MINB, bool SUMM>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 fg_warp_kernel(const __grid_constant__ FgConst c, int B, const double *__restrict__ x, long ldx,
-               double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG) {
+               double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG,
+               double *__restrict__ S, long ldS) {
     extern __shared__ __align__(16) double smem[];
     const int ts = c.ts;
     const int nt = (ts + 31) >> 5;
@@ -677,7 +736,7 @@ fg_warp_kernel(const __grid_constant__ FgConst c, int B, const double *__restric
     slice_prefetch(wsm, x + (size_t)b * ldx, 1 + PX * (min(32, ts) + 1), lane);
     cp_async_commit();
     if (needG && lane < NBUF * NPP) record_init(tile + lane * REC);
-    double dt = 0.0, n0 = 0.0, accT = 0.0, accp = 0.0;
+    double dt = 0.0, n0 = 0.0, accT = 0.0, accp = 0.0, accm = 0.0, accq = 0.0;
 #pragma unroll 1
     while (b < B) {
         int nb = b, ntile = t + 1;
@@ -702,15 +761,19 @@ fg_warp_kernel(const __grid_constant__ FgConst c, int B, const double *__restric
         }
         const double ne = (t == nt - 1 && lane < PX) ? sx[1 + PX * nk + lane] : 0.0;
         double *Fb = F + (size_t)b * ldF, *Gb = G + (size_t)b * ldG;
-        double sumT, sump;
-        tile_eval_call<FORM, WIND>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, sumT, sump);
-        accT += sumT;
-        accp += sump;
+        TileSums tsum;
+        tile_eval_call<FORM, WIND, SUMM>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, tsum);
+        accT += tsum.sumT;
+        accp += tsum.sump;
+        accm = fmax(accm, tsum.dmax);
+        accq += tsum.dssq;
         if (t == nt - 1) {
             const double tT = warp_sum(accT);
             const double tp = FORM == TOLCUDA_FORM_S10 ? warp_sum(accp) : 0.0;
-            traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG);
-            accT = accp = 0.0;
+            const double dmax = SUMM ? warp_max(accm) : 0.0, dssq = SUMM ? warp_sum(accq) : 0.0;
+            traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG, dmax, dssq,
+                                SUMM ? S + (size_t)b * ldS : nullptr);
+            accT = accp = accm = accq = 0.0;
         }
         __syncwarp();
         b = nb;
@@ -720,9 +783,9 @@ fg_warp_kernel(const __grid_constant__ FgConst c, int B, const double *__restric
     cp_async_wait<0>();
 }
 
-template <int FORM, int WIND, int MAXT, int MINB>
+template <int FORM, int WIND, int MAXT, int MINB, bool SUMM>
 cudaError_t launch_cta(const FgLaunch &L) {
-    auto kern = fg_cta_kernel<FORM, WIND, MAXT, MINB>;
+    auto kern = fg_cta_kernel<FORM, WIND, MAXT, MINB, SUMM>;
     const int nthr = 32 * ((L.c->ts + 31) / 32);
     const size_t smem = sizeof(double) * (size_t)(nthr / 32) * WARP_SMEM;
     static size_t configured = 0;  // per instantiation
@@ -731,13 +794,13 @@ cudaError_t launch_cta(const FgLaunch &L) {
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    kern<<<L.B, nthr, smem, L.stream>>>(*L.c, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG);
+    kern<<<L.B, nthr, smem, L.stream>>>(*L.c, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG, L.S, L.ldS);
     return cudaGetLastError();
 }
 
-template <int FORM, int WIND, int WARPS, int MINB>
+template <int FORM, int WIND, int WARPS, int MINB, bool SUMM>
 cudaError_t launch_warp(const FgLaunch &L) {
-    auto kern = fg_warp_kernel<FORM, WIND, WARPS, MINB>;
+    auto kern = fg_warp_kernel<FORM, WIND, WARPS, MINB, SUMM>;
     const size_t smem = sizeof(double) * (size_t)WARPS * WARP_SMEM_B;
     static bool configured = false;
     if (!configured) {
@@ -748,19 +811,26 @@ cudaError_t launch_warp(const FgLaunch &L) {
     const int resident = L.sm_count * MINB;  // persistent: one wave of CTAs
     const int want = (L.B + WARPS - 1) / WARPS;
     const int grid = want < resident ? want : resident;
-    kern<<<grid, WARPS * 32, smem, L.stream>>>(*L.c, L.B, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG);
+    kern<<<grid, WARPS * 32, smem, L.stream>>>(*L.c, L.B, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG,
+                                               L.S, L.ldS);
     return cudaGetLastError();
 }
 
-template <int FORM, int WIND>
-cudaError_t launch_any(const FgLaunch &L) {
+template <int FORM, int WIND, bool SUMM>
+cudaError_t launch_sel(const FgLaunch &L) {
     // Kernel A (one CTA per trajectory) needs the whole trajectory in one CTA at a register budget that
     // does not spill: ts <= 256.  Longer trajectories, and L.kernel == 2, take kernel B, whose warps walk
     // the tiles of a trajectory one after the other (any ts).
     const int ts = L.c->ts;
-    if (L.kernel == 2 || ts > 256) return launch_warp<FORM, WIND, 4, 4>(L);  // 128 registers, 16 warps / SM
-    if (ts <= 128) return launch_cta<FORM, WIND, 128, 4>(L);                 // 128 registers, 16 warps / SM
-    return launch_cta<FORM, WIND, 256, 2>(L);                                // 128 registers, 14-16 warps / SM
+    if (L.kernel == 2 || ts > 256) return launch_warp<FORM, WIND, 4, 4, SUMM>(L);  // 128 registers, 16 warps / SM
+    if (ts <= 128) return launch_cta<FORM, WIND, 128, 4, SUMM>(L);                 // 128 registers, 16 warps / SM
+    return launch_cta<FORM, WIND, 256, 2, SUMM>(L);                          // 128 registers, 14-16 warps / SM
+}
+
+// the per-trajectory summary is a separate instantiation so that plain F/G launches pay nothing for it
+template <int FORM, int WIND>
+cudaError_t launch_any(const FgLaunch &L) {
+    return L.S ? launch_sel<FORM, WIND, true>(L) : launch_sel<FORM, WIND, false>(L);
 }
 
 }  // namespace

@@ -19,6 +19,8 @@ struct FgLaunch {
     double *G;
     long ldG;
     int needF, needG;
+    double *S;  // optional per-trajectory summary [B][ldS >= 4]: objective, max|defect|, max|boundary|, sum defect^2
+    long ldS;
     int kernel;    // 0/1 = kernel A (CTA per trajectory), 2 = kernel B (persistent warps)
     int sm_count;  // SMs of the device
     cudaStream_t stream;

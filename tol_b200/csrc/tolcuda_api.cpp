@@ -39,7 +39,7 @@ using namespace tolcuda;
 // the stream that carries H2D -> kernel -> D2H for that chunk.
 struct BatchLane {
     cudaStream_t stream = nullptr;
-    double *d_x = nullptr, *d_F = nullptr, *d_G = nullptr;
+    double *d_x = nullptr, *d_F = nullptr, *d_G = nullptr, *d_S = nullptr;
     int cap = 0;  // trajectories
 };
 
@@ -69,8 +69,9 @@ tolcuda_ctx *g_bound = nullptr;
 long round_up(long v, long m) { return (v + m - 1) / m * m; }
 
 int launch(tolcuda_ctx *h, cudaStream_t st, int B, const double *x, long ldx, double *F, long ldF,
-           double *G, long ldG, int needF, int needG) {
+           double *G, long ldG, int needF, int needG, double *S = nullptr, long ldS = 0) {
     FgLaunch L;
+    L.S = S, L.ldS = ldS;
     L.c = &h->c;
     L.B = B;
     L.x = x, L.ldx = ldx, L.F = F, L.ldF = ldF, L.G = G, L.ldG = ldG;
@@ -88,6 +89,7 @@ void free_lane(BatchLane &l) {
     if (l.d_x) cudaFree(l.d_x);
     if (l.d_F) cudaFree(l.d_F);
     if (l.d_G) cudaFree(l.d_G);
+    if (l.d_S) cudaFree(l.d_S);
     if (l.stream) cudaStreamDestroy(l.stream);
     l = BatchLane();
 }
@@ -98,13 +100,15 @@ int ensure_lane(tolcuda_ctx *h, BatchLane &l, int cap) {
     if (l.d_x) cudaFree(l.d_x);
     if (l.d_F) cudaFree(l.d_F);
     if (l.d_G) cudaFree(l.d_G);
-    l.d_x = l.d_F = l.d_G = nullptr;
+    if (l.d_S) cudaFree(l.d_S);
+    l.d_x = l.d_F = l.d_G = l.d_S = nullptr;
     l.cap = 0;
     const long ldx = tolcuda_padded_ld(h->c.n), ldF = tolcuda_padded_ld(h->c.neF),
                ldG = tolcuda_padded_ld(h->c.neG);
     CU(cudaMalloc(&l.d_x, sizeof(double) * ldx * cap));
     CU(cudaMalloc(&l.d_F, sizeof(double) * ldF * cap));
     CU(cudaMalloc(&l.d_G, sizeof(double) * ldG * cap));
+    CU(cudaMalloc(&l.d_S, sizeof(double) * 4 * cap));
     l.cap = cap;
     return 0;
 }
@@ -423,11 +427,16 @@ int tolcuda_eval(tolcuda_handle h, const double *x, int needF, double *F, int ne
 
 int tolcuda_eval_batch(tolcuda_handle h, int B, const double *x, long ldx, double *F, long ldF,
                        double *G, long ldG, int flags) {
-    if (!h || B < 0) return TOLCUDA_EINVAL;
+    return tolcuda_eval_batch_summary(h, B, x, ldx, F, ldF, G, ldG, nullptr, 0, flags);
+}
+
+int tolcuda_eval_batch_summary(tolcuda_handle h, int B, const double *x, long ldx, double *F, long ldF,
+                               double *G, long ldG, double *summary, long lds, int flags) {
+    if (!h || B < 0 || (summary && lds < 4)) return TOLCUDA_EINVAL;
     const int needF = (flags & TOLCUDA_NEED_F) != 0;
     // bits 8.. of flags: kernel experiment switches (undocumented, tools/kbench.py only)
     const int needG = (flags & TOLCUDA_NEED_G) ? (1 | (((flags >> 8) & 0xff) << 1)) : 0;
-    if (B == 0 || (!needF && !needG)) return 0;
+    if (B == 0 || (!needF && !needG && !summary)) return 0;
     const FgConst &c = h->c;
     if (!x || ldx < c.n || (needF && (!F || ldF < c.neF)) || (needG && (!G || ldG < c.neG))) {
         set_error("tolcuda_eval_batch: null pointer or leading dimension shorter than the row");
@@ -446,7 +455,7 @@ int tolcuda_eval_batch(tolcuda_handle h, int B, const double *x, long ldx, doubl
         }
     }
     if (!host) {
-        int rc = launch(h, h->stream, B, x, ldx, F, ldF, G, ldG, needF, needG);
+        int rc = launch(h, h->stream, B, x, ldx, F, ldF, G, ldG, needF, needG, summary, lds);
         if (rc) return rc;
         if (!(flags & TOLCUDA_NO_SYNC)) CU(cudaStreamSynchronize(h->stream));
         return 0;
@@ -475,11 +484,15 @@ int tolcuda_eval_batch(tolcuda_handle h, int B, const double *x, long ldx, doubl
         const int nb = std::min(chunk, B - b0);
         CU(cudaMemcpy2DAsync(l.d_x, sizeof(double) * dldx, x + (size_t)b0 * ldx, sizeof(double) * ldx,
                              sizeof(double) * c.n, nb, cudaMemcpyHostToDevice, l.stream));
-        int rc = launch(h, l.stream, nb, l.d_x, dldx, l.d_F, dldF, l.d_G, dldG, needF, needG);
+        int rc = launch(h, l.stream, nb, l.d_x, dldx, l.d_F, dldF, l.d_G, dldG, needF, needG,
+                        summary ? l.d_S : nullptr, 4);
         if (rc) return rc;
         if (needF)
             CU(cudaMemcpy2DAsync(F + (size_t)b0 * ldF, sizeof(double) * ldF, l.d_F, sizeof(double) * dldF,
                                  sizeof(double) * c.neF, nb, cudaMemcpyDeviceToHost, l.stream));
+        if (summary)
+            CU(cudaMemcpy2DAsync(summary + (size_t)b0 * lds, sizeof(double) * lds, l.d_S, sizeof(double) * 4,
+                                 sizeof(double) * 4, nb, cudaMemcpyDeviceToHost, l.stream));
         if (needG)
             CU(cudaMemcpy2DAsync(G + (size_t)b0 * ldG, sizeof(double) * ldG, l.d_G, sizeof(double) * dldG,
                                  sizeof(double) * c.neG, nb, cudaMemcpyDeviceToHost, l.stream));

@@ -171,6 +171,19 @@ class Evaluator:
         _l.check(self.L.tolcuda_eval_batch(self.h, B, X.data_ptr(), X.stride(0), F.data_ptr(), F.stride(0),
                                            G.data_ptr(), G.stride(0), flags))
 
+    def summary_host(self, X, needF=False, needG=False):
+        """tolcuda_eval_batch_summary with host arrays: [B, 4] = objective, max|defect|, max boundary
+        violation, sum defect^2 (F and G are not produced unless asked for)"""
+        B = X.shape[0]
+        S = np.empty((B, 4))
+        F = np.empty((B, self.neF)) if needF else None
+        G = np.empty((B, self.neG)) if needG else None
+        flags = (NEED_F if needF else 0) | (NEED_G if needG else 0) | HOST_PTRS
+        _l.check(self.L.tolcuda_eval_batch_summary(
+            self.h, B, X.ctypes.data, X.strides[0] // 8, F.ctypes.data if needF else None, self.neF,
+            G.ctypes.data if needG else None, self.neG, S.ctypes.data, 4, flags))
+        return S, F, G
+
     def set_stream(self, cuda_stream_ptr):
         """cudaStream_t as an integer (torch: stream.cuda_stream; 0 = legacy default stream)"""
         _l.check(self.L.tolcuda_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
