@@ -40,6 +40,10 @@ extern "C" {
 /* neither pointer flag: detected with cudaPointerGetAttributes on x */
 #define TOLCUDA_NO_SYNC 0x40 /* device pointers only: return after enqueueing on the context's
                                 stream instead of synchronising it                         */
+#define TOLCUDA_COMPACT_G 0x80 /* G receives COMPACT rows (tolcuda_compact_len doubles each, see
+                                  tolcuda_expand_compact_g) instead of rows in coordinate order */
+#define TOLCUDA_FULL_G_COPY 0x100 /* host pointers only: copy full G rows across PCIe instead of
+                                     compact rows expanded by host threads (see tolcuda_eval_batch) */
 
 typedef struct tolcuda_ctx *tolcuda_handle;
 
@@ -130,8 +134,30 @@ int tolcuda_eval(tolcuda_handle h, const double *x, int needF, double *F, int ne
  * (n doubles) and writes F + b*ldF (neF doubles) and G + b*ldG (neG doubles, coordinate order of
  * tolcuda_pattern).  Leading dimensions are in doubles; padding them to a multiple of 16 keeps
  * every trajectory 128-byte aligned (tolcuda_padded_ld).  flags: TOLCUDA_NEED_* | pointer kind. */
+/* Host pointers: chunks of trajectories are pipelined H2D(x) -> kernel -> D2H(F, G) over three streams.
+ * 71 of the 104 G values of a collocation window are structural constants (the zeros and +-1 of reference
+ * tabG, src/problem.cpp:1038,1084,1098,1112,1170,1182,1204) and two equal -dt, so by default only the
+ * x-dependent values cross PCIe (compact rows) and a pool of host threads places them in the caller's G
+ * and writes the constants as literals; the rows the caller sees are bit for bit those of the
+ * device-pointer path.  TOLCUDA_FULL_G_COPY (or environment TOLCUDA_COMPACT=0) copies full rows instead. */
 int tolcuda_eval_batch(tolcuda_handle h, int B, const double *x, long ldx, double *F, long ldF,
                        double *G, long ldG, int flags);
+
+/* Compact G rows, for callers that move G themselves (e.g. gather it from several GPUs):
+ *   [0, R0)                    objective-row block as in G (R0 = 3*ts+4 for S10, ts+6 for G7)
+ *   [R0 + 31*k, R0 + 31*k+31)  the 31 x-dependent values of window k in coordinate order
+ *   [R0 + 31*ts, + nbG)        boundary block as in G (nbG = 33 for S10, 42 for G7)
+ *   [R0 + 31*ts + nbG]         -dt (value of the d/d(dphi) and d/d(dCL) entries of rows F7, F8)
+ * tolcuda_compact_len returns the row length (or a negative TOLCUDA_E* code); tolcuda_eval_batch with
+ * TOLCUDA_COMPACT_G writes such rows (ldG >= that length); tolcuda_expand_compact_g turns B of them into
+ * rows in the coordinate order of tolcuda_pattern on `threads` host threads (0 = all cores available to
+ * the process).  Host memory only, no CUDA call; no arithmetic on the values. */
+long tolcuda_compact_len(int formulation, int ts);
+int tolcuda_expand_compact_g(int formulation, int ts, long B, const double *Gc, long ldGc, double *G, long ldG,
+                             int threads);
+/* host threads the host-pointer batch path of this context expands compact rows with (0 = default:
+ * environment TOLCUDA_HOST_THREADS, else the cores available to the process / LOCAL_WORLD_SIZE) */
+int tolcuda_set_host_threads(tolcuda_handle h, int threads);
 
 /* Same evaluation plus a per-trajectory summary computed inside the kernel from values it already holds
  * (a device-side consumer of F; nothing of the kind exists in the reference, where SNOPT alone reads F):

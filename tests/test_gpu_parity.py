@@ -105,6 +105,45 @@ def test_batch_host_pointers_chunked(name, monkeypatch):
     ev.close()
 
 
+@pytest.mark.parametrize("name", ["S10_tempest_ts200", "G7_skywalker_ts100", "S10_tempesteric_ts33", "S10_tempest_ts1",
+                                  "G7_skywalker_ts2", "S10_tempest_ts100_wind3"])
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_compact_rows_path_equals_full_rows(name, kernel, monkeypatch):
+    """The host-pointer path moves G across PCIe as compact rows (x-dependent values only) and expands them
+    on host threads.  Its rows must be BIT-IDENTICAL to full rows copied from the device (TOLCUDA_FULL_G_COPY),
+    for aligned and 8-byte-shifted destinations, through several chunks and lanes; compact rows requested
+    by the caller (TOLCUDA_COMPACT_G, host and device pointers) expand to the same rows too."""
+    monkeypatch.setenv("TOLCUDA_KERNEL", str(kernel))
+    monkeypatch.setenv("TOLCUDA_CHUNK_MB", "1")
+    g = load_golden(name)
+    m, ts = str(g["mission"]), int(g["ts"])
+    ev = T.Evaluator.from_golden(g)
+    B = 101
+    X = T.synth.batch(g["x"][0], 4242, 0, B)
+    Ff, Gf = ev.eval_batch_host(X, full_copy=True)
+    Fc, Gc = ev.eval_batch_host(X)
+    assert np.array_equal(Fc.view(np.int64), Ff.view(np.int64))
+    assert np.array_equal(Gc.view(np.int64), Gf.view(np.int64))
+    # destination rows 8 bytes off 16-byte alignment, padding untouched; G only
+    buf = np.full((B, ev.neG + 3), np.nan)
+    ev.set_host_threads(3)
+    ev.eval_batch_host(X, None, buf[:, 1:1 + ev.neG], needF=False)
+    assert np.array_equal(buf[:, 1:1 + ev.neG].view(np.int64), Gf.view(np.int64))
+    assert np.isnan(buf[:, 0]).all() and np.isnan(buf[:, 1 + ev.neG:]).all()
+    # caller-visible compact rows
+    _, Gr = ev.eval_batch_host(X, compact_rows=True)
+    assert Gr.shape == (B, T.evaluator.compact_len(m, ts))
+    assert np.array_equal(T.evaluator.expand_compact_g(m, ts, Gr).view(np.int64), Gf.view(np.int64))
+    Xd = _dev(X)
+    Fd = torch.empty(B, ev.neF, dtype=torch.float64, device="cuda")
+    Gd = torch.full((B, ev.compact_len + 5), float("nan"), dtype=torch.float64, device="cuda")
+    ev.eval_batch_device(Xd, Fd, Gd, compact_rows=True)
+    Gdh = Gd.cpu().numpy()
+    assert np.array_equal(Gdh[:, :ev.compact_len].view(np.int64), Gr.view(np.int64)) and np.isnan(Gdh[:, ev.compact_len:]).all()
+    assert np.array_equal(Fd.cpu().numpy().view(np.int64), Ff.view(np.int64))
+    ev.close()
+
+
 @pytest.mark.parametrize("name,seed0", [("G7_skywalker_ts100", T.synth.SEED_G7),
                                         ("S10_tempest_ts200", T.synth.SEED_S10)])
 @pytest.mark.parametrize("kernel", [1, 2])

@@ -117,3 +117,66 @@ def test_bounds_are_bit_identical_to_reference_setlimits(name):
     xl, xu, fl, fu = T.bounds(_cfg_from_golden(g))
     for got, key in ((xl, "xlow"), (xu, "xupp"), (fl, "Flow"), (fu, "Fupp")):
         assert np.array_equal(got, g[key]), key
+
+
+# record positions (within a window's 104 G values, row-major over the 8 defect rows x 13 columns) whose
+# value depends on x; derived here from the reference fixtures themselves, not from the library
+def _varying_positions():
+    var = np.zeros(104, bool)
+    for name in GOLDEN:
+        g = load_golden(name)
+        if int(g["wind_model"]) != 1:
+            continue
+        ts = int(g["ts"])
+        R0 = int(g["neG"]) - 104 * ts - (42 if str(g["mission"]) == "G7" else 33)
+        rec = g["G"][:, R0:R0 + 104 * ts].reshape(-1, 104)
+        var |= ~((rec == 0).all(axis=0) | (rec == 1).all(axis=0) | (rec == -1).all(axis=0))
+    return var
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+@pytest.mark.parametrize("shift", [0, 1])
+def test_compact_rows_expand_to_reference_rows(name, shift):
+    """tolcuda_expand_compact_g (the host half of the host-pointer batch path): compact rows cut out of the
+    REFERENCE's G expand back to the reference's G exactly, constants included; shift=1 puts the
+    destination rows 8 bytes off 16-byte alignment (the other store path)"""
+    g = load_golden(name)
+    m, ts, neG = str(g["mission"]), int(g["ts"]), int(g["neG"])
+    nbG = 42 if m == "G7" else 33
+    R0 = neG - 104 * ts - nbG
+    var = _varying_positions()
+    mdt_pos = [87, 101]  # d/d(dphi) of row F7, d/d(dCL) of row F8: -dt (src/problem.cpp:1171-1172, 1183-1184)
+    var[mdt_pos] = False
+    pos = np.where(var)[0]
+    assert pos.size == 31
+    Lc = T.evaluator.compact_len(m, ts)
+    assert Lc == R0 + 31 * ts + nbG + 1
+    G = g["G"].copy()
+    G[:, g["ub_mask"]] = 0.0  # the reference leaves these uninitialised; defined as 0.0
+    B = G.shape[0]
+    Gc = np.full((B, Lc + 3), np.nan)
+    Gc[:, :R0] = G[:, :R0]
+    Gc[:, R0:R0 + 31 * ts] = G[:, R0:R0 + 104 * ts].reshape(B, ts, 104)[:, :, pos].reshape(B, -1)
+    Gc[:, R0 + 31 * ts:R0 + 31 * ts + nbG] = G[:, neG - nbG:]
+    Gc[:, R0 + 31 * ts + nbG] = -g["x"][:, 0]
+    buf = np.full((B, neG + 4), np.nan)
+    out = buf[:, shift:shift + neG]
+    T.evaluator.expand_compact_g(m, ts, Gc, out, threads=3)
+    assert np.array_equal(out, G)
+    assert np.array_equal(out.view(np.int64), G.view(np.int64))  # bit for bit: structural zeros are +0.0
+    assert np.isnan(buf[:, :shift]).all() and np.isnan(buf[:, shift + neG:]).all()
+
+
+def test_compact_expand_many_rows_threads():
+    """more rows than work items per thread, odd thread counts, B = 0"""
+    m, ts = "S10", 7
+    _, _, neG = T.problem_dims(m, ts)
+    Lc = T.evaluator.compact_len(m, ts)
+    rng = np.random.default_rng(3)
+    Gc = rng.standard_normal((1001, Lc))
+    ref = T.evaluator.expand_compact_g(m, ts, Gc, threads=1)
+    for th in (2, 5, 16):
+        assert np.array_equal(T.evaluator.expand_compact_g(m, ts, Gc, threads=th), ref)
+    assert T.evaluator.expand_compact_g(m, ts, Gc[:0]).shape == (0, neG)
+    with pytest.raises(T.TolcudaError):
+        T.evaluator.expand_compact_g(m, ts, Gc[:, :Lc - 1].copy())

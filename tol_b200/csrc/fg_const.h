@@ -13,6 +13,7 @@
 #define TOLCUDA_PX 11      /* numinp,    problems/<M>/snopt.param line 3 */
 #define TOLCUDA_PF 8       /* numstates, problems/<M>/snopt.param line 4 */
 #define TOLCUDA_REC 104    /* G values per collocation window: 8 defect rows x 13 columns */
+#define TOLCUDA_NVAR 31    /* of which depend on x (two more are -dt, the rest 0 or +-1) */
 
 struct FgConst {
     int form, ts, wind, nb;

@@ -55,7 +55,11 @@ constexpr int TILE_LEN = NBUF * NPP * REC;  // 832 doubles
 constexpr int WARP_SMEM = SX_LEN + TILE_LEN;        // kernel A
 constexpr int WARP_SMEM_B = 2 * SX_LEN + TILE_LEN;  // kernel B: double-buffered x slice
 constexpr int F_LD = 10;               // smem stride of a window's 8 defects (== 2 mod 4)
-constexpr int NVAR = 31;               // x-dependent entries of a record (plus two -dt entries)
+constexpr int NVAR = TOLCUDA_NVAR;     // x-dependent entries of a record (plus two -dt entries)
+// kernel flavours: plain F/G; F/G + per-trajectory summary; F + COMPACT G (objective-row block, then the
+// NVAR x-dependent entries of every window, then the boundary block) for the host-pointer path, where the
+// structural constants are filled in on the host instead of crossing PCIe
+constexpr int MODE_PLAIN = 0, MODE_SUMMARY = 1, MODE_COMPACT = 2;
 
 // per-lane partial results a tile hands back: cost sums and the feasibility summary of its defects
 struct TileSums {
@@ -250,7 +254,7 @@ __device__ __forceinline__ void wind_cube(const FgConst &c, const double xn, con
 // tile: the warp's NBUF x NPP record slots, constants already in place (record_init).
 // needG carries two experiment switches in bits 2 and 3 (tools/kbench.py): 4 = stage but do not store
 // G, 8 = no trigonometry.
-template <int FORM, int WIND, bool SUMM>
+template <int FORM, int WIND, int MODE>
 __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *tile, const double dt,
                                           const int k0, const int nk, const int lane,
                                           double *__restrict__ Fb, double *__restrict__ Gb,
@@ -383,7 +387,7 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
         f[7] = s1[7] - dCL * dt - s0[7];
     }
     ts_out.dmax = 0.0, ts_out.dssq = 0.0;
-    if (SUMM) {
+    if (MODE == MODE_SUMMARY) {
         double m = 0.0, q = 0.0;
         if (active) {
 #pragma unroll
@@ -495,6 +499,38 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
     v[29] = -dphi;  // F7 :1172
     v[30] = -dCL;   // F8 :1184
 
+    if (MODE == MODE_COMPACT) {
+        // compact G: the warp's windows as NVAR doubles each, contiguous at Gb + R0 + NVAR*k; staged in the
+        // tile half a warp at a time (lane stride 31 doubles: conflict-free) and sent as one bulk copy
+        double *Gc = Gb + c.R0 + (size_t)NVAR * k0;
+#pragma unroll 1
+        for (int hf = 0; hf < 2; hf++) {
+            if (16 * hf >= nk) break;
+            if ((lane >> 4) == hf) {
+                double *q = tile + (lane & 15) * NVAR;
+#pragma unroll
+                for (int i = 0; i < NVAR; i++) q[i] = v[i];
+            }
+            const int cnt = min(16, nk - 16 * hf) * NVAR;
+            double *dst = Gc + (size_t)NVAR * 16 * hf;
+            const bool bulkc = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((cnt & 1) == 0);
+            if (bulkc) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    bulk_store(dst, tile, cnt * 8);
+                    bulk_wait_read<0>();
+                }
+                __syncwarp();
+            } else {
+                __syncwarp();
+                for (int i = lane; i < cnt; i += 32) dst[i] = tile[i];
+                __syncwarp();
+            }
+        }
+        return;
+    }
+
     // ---- drain: groups of NPP windows through the two record buffers, whole records to global ----
     // Group g (windows k0+NPP*g ..) fills buffer g&1 while the TMA unit may still be reading the other
     // one; lane 0 issues every bulk copy (NPP contiguous records = NPP*832 bytes) and owns the bulk
@@ -533,12 +569,12 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
 
 // Out-of-line instance for the persistent kernel: inlined into its trajectory/tile loop, ptxas keeps
 // dozens of extra values live across the loop and spills; as a call the tile body is allocated on its own.
-template <int FORM, int WIND, bool SUMM>
+template <int FORM, int WIND, int MODE>
 __device__ __noinline__ void tile_eval_call(const FgConst &c, double *sx, double *tile, const double dt,
                                             const int k0, const int nk, const int lane,
                                             double *__restrict__ Fb, double *__restrict__ Gb,
                                             const int needF, const int needG, TileSums &ts_out) {
-    tile_eval<FORM, WIND, SUMM>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, ts_out);
+    tile_eval<FORM, WIND, MODE>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, ts_out);
 }
 
 // ---- end of a trajectory: F[0], boundary rows, objective-row ends --------------------------------------
@@ -550,12 +586,14 @@ __device__ __forceinline__ void traj_epilogue(const FgConst &c, const int lane, 
                                               const double tT, const double tp, const double n0,
                                               const double ne, double *__restrict__ Fb,
                                               double *__restrict__ Gb, const int needF, const int needG,
-                                              const double dmax, const double dssq, double *__restrict__ Sb) {
+                                              const double dmax, const double dssq, double *__restrict__ Sb,
+                                              const int recw = REC) {
     constexpr bool S10 = (FORM == TOLCUDA_FORM_S10);
     const int ts = c.ts;
     double f0 = 0.0, bval = 0.0;  // objective (lane 0) and this lane's boundary-row value
     double *Fbnd = Fb + (c.neF - c.nb);
-    double *Gbnd = Gb + c.R0 + (size_t)REC * ts;
+    double *Gbnd = Gb + c.R0 + (size_t)recw * ts;  // recw = NVAR in the compact layout
+    if (recw != REC && needG && lane == 0) Gbnd[c.nbG] = -dt;  // compact rows end with the records' -dt entry
     if (S10) {
         if (needF) {
             if (lane == 0) Fb[0] = c.half_kT * tT + c.half_kp * tp + c.kdt * dt;  // src/problemS10.cpp:264
@@ -644,11 +682,12 @@ __device__ __forceinline__ void traj_epilogue(const FgConst &c, const int lane, 
 // grid.x = B, blockDim.x = 32*ceil(ts/32) (<= MAXT).  Warp w owns windows 32w..32w+31 and runs on its
 // own after start-up; the cost sum crosses warps through shared memory and an arrival counter, and the
 // last warp to arrive runs the trajectory epilogue.
-template <int FORM, int WIND, int MAXT, int MINB, bool SUMM>
+template <int FORM, int WIND, int MAXT, int MINB, int MODE>
 __global__ void __launch_bounds__(MAXT, MINB)
 fg_cta_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, long ldx,
               double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG,
               double *__restrict__ S, long ldS) {
+    constexpr bool SUMM = (MODE == MODE_SUMMARY);
     extern __shared__ __align__(16) double smem[];
     __shared__ double red[SUMM ? 4 : 2][32];
     __shared__ int arrivals;
@@ -679,7 +718,7 @@ fg_cta_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, l
     __syncwarp();
 
     TileSums tsum;
-    tile_eval<FORM, WIND, SUMM>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, tsum);
+    tile_eval<FORM, WIND, MODE>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, tsum);
 
     // cost sums: warp shuffle, then across warps through shared memory
     const double sumT = warp_sum(tsum.sumT);
@@ -709,7 +748,8 @@ fg_cta_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, l
             dssq += vred[96 + w];
         }
     }
-    traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG, dmax, dssq, SUMM ? S + b * ldS : nullptr);
+    traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG, dmax, dssq, SUMM ? S + b * ldS : nullptr,
+                        MODE == MODE_COMPACT ? NVAR : REC);
 }
 
 // ---- kernel B: persistent warps, one trajectory per warp at a time ------------------------------------------
@@ -718,11 +758,12 @@ fg_cta_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, l
 // tiles in order, so cost sums stay in registers and no warp ever waits for another.  While a tile is
 // evaluated, the x slice of the next tile (or of the next trajectory's first tile) is already in flight
 // (cp.async) into the other slice buffer.  Selectable variant (TOLCUDA_KERNEL=2).
-template <int FORM, int WIND, int WARPS, int MINB, bool SUMM>
+template <int FORM, int WIND, int WARPS, int MINB, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 fg_warp_kernel(const __grid_constant__ FgConst c, int B, const double *__restrict__ x, long ldx,
                double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG,
                double *__restrict__ S, long ldS) {
+    constexpr bool SUMM = (MODE == MODE_SUMMARY);
     extern __shared__ __align__(16) double smem[];
     const int ts = c.ts;
     const int nt = (ts + 31) >> 5;
@@ -762,7 +803,7 @@ fg_warp_kernel(const __grid_constant__ FgConst c, int B, const double *__restric
         const double ne = (t == nt - 1 && lane < PX) ? sx[1 + PX * nk + lane] : 0.0;
         double *Fb = F + (size_t)b * ldF, *Gb = G + (size_t)b * ldG;
         TileSums tsum;
-        tile_eval_call<FORM, WIND, SUMM>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, tsum);
+        tile_eval_call<FORM, WIND, MODE>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, tsum);
         accT += tsum.sumT;
         accp += tsum.sump;
         accm = fmax(accm, tsum.dmax);
@@ -772,7 +813,7 @@ fg_warp_kernel(const __grid_constant__ FgConst c, int B, const double *__restric
             const double tp = FORM == TOLCUDA_FORM_S10 ? warp_sum(accp) : 0.0;
             const double dmax = SUMM ? warp_max(accm) : 0.0, dssq = SUMM ? warp_sum(accq) : 0.0;
             traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG, dmax, dssq,
-                                SUMM ? S + (size_t)b * ldS : nullptr);
+                                SUMM ? S + (size_t)b * ldS : nullptr, MODE == MODE_COMPACT ? NVAR : REC);
             accT = accp = accm = accq = 0.0;
         }
         __syncwarp();
@@ -783,9 +824,9 @@ fg_warp_kernel(const __grid_constant__ FgConst c, int B, const double *__restric
     cp_async_wait<0>();
 }
 
-template <int FORM, int WIND, int MAXT, int MINB, bool SUMM>
+template <int FORM, int WIND, int MAXT, int MINB, int MODE>
 cudaError_t launch_cta(const FgLaunch &L) {
-    auto kern = fg_cta_kernel<FORM, WIND, MAXT, MINB, SUMM>;
+    auto kern = fg_cta_kernel<FORM, WIND, MAXT, MINB, MODE>;
     const int nthr = 32 * ((L.c->ts + 31) / 32);
     const size_t smem = sizeof(double) * (size_t)(nthr / 32) * WARP_SMEM;
     static size_t configured = 0;  // per instantiation
@@ -798,9 +839,9 @@ cudaError_t launch_cta(const FgLaunch &L) {
     return cudaGetLastError();
 }
 
-template <int FORM, int WIND, int WARPS, int MINB, bool SUMM>
+template <int FORM, int WIND, int WARPS, int MINB, int MODE>
 cudaError_t launch_warp(const FgLaunch &L) {
-    auto kern = fg_warp_kernel<FORM, WIND, WARPS, MINB, SUMM>;
+    auto kern = fg_warp_kernel<FORM, WIND, WARPS, MINB, MODE>;
     const size_t smem = sizeof(double) * (size_t)WARPS * WARP_SMEM_B;
     static bool configured = false;
     if (!configured) {
@@ -816,21 +857,22 @@ cudaError_t launch_warp(const FgLaunch &L) {
     return cudaGetLastError();
 }
 
-template <int FORM, int WIND, bool SUMM>
+template <int FORM, int WIND, int MODE>
 cudaError_t launch_sel(const FgLaunch &L) {
     // Kernel A (one CTA per trajectory) needs the whole trajectory in one CTA at a register budget that
     // does not spill: ts <= 256.  Longer trajectories, and L.kernel == 2, take kernel B, whose warps walk
     // the tiles of a trajectory one after the other (any ts).
     const int ts = L.c->ts;
-    if (L.kernel == 2 || ts > 256) return launch_warp<FORM, WIND, 4, 4, SUMM>(L);  // 128 registers, 16 warps / SM
-    if (ts <= 128) return launch_cta<FORM, WIND, 128, 4, SUMM>(L);                 // 128 registers, 16 warps / SM
-    return launch_cta<FORM, WIND, 256, 2, SUMM>(L);                          // 128 registers, 14-16 warps / SM
+    if (L.kernel == 2 || ts > 256) return launch_warp<FORM, WIND, 4, 4, MODE>(L);  // 128 registers, 16 warps / SM
+    if (ts <= 128) return launch_cta<FORM, WIND, 128, 4, MODE>(L);                 // 128 registers, 16 warps / SM
+    return launch_cta<FORM, WIND, 256, 2, MODE>(L);                          // 128 registers, 14-16 warps / SM
 }
 
 // the per-trajectory summary is a separate instantiation so that plain F/G launches pay nothing for it
 template <int FORM, int WIND>
 cudaError_t launch_any(const FgLaunch &L) {
-    return L.S ? launch_sel<FORM, WIND, true>(L) : launch_sel<FORM, WIND, false>(L);
+    if (L.compact) return launch_sel<FORM, WIND, MODE_COMPACT>(L);
+    return L.S ? launch_sel<FORM, WIND, MODE_SUMMARY>(L) : launch_sel<FORM, WIND, MODE_PLAIN>(L);
 }
 
 }  // namespace

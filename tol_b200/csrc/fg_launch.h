@@ -21,6 +21,7 @@ struct FgLaunch {
     int needF, needG;
     double *S;  // optional per-trajectory summary [B][ldS >= 4]: objective, max|defect|, max|boundary|, sum defect^2
     long ldS;
+    int compact;  // G/ldG address the compact layout [R0 | 31 per window | boundary block] (host-pointer path)
     int kernel;    // 0/1 = kernel A (CTA per trajectory), 2 = kernel B (persistent warps)
     int sm_count;  // SMs of the device
     cudaStream_t stream;

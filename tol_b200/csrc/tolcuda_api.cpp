@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <new>
 
@@ -39,9 +40,14 @@ using namespace tolcuda;
 // the stream that carries H2D -> kernel -> D2H for that chunk.
 struct BatchLane {
     cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;  // the lane's last D2H has landed
     double *d_x = nullptr, *d_F = nullptr, *d_G = nullptr, *d_S = nullptr;
-    int cap = 0;  // trajectories
+    double *h_Gc = nullptr;  // pinned landing area of compact G rows, expanded from here into the caller's G
+    int cap = 0;             // trajectories
+    long ldG = 0;            // row length d_G was allocated for (full or compact rows)
+    long ldGc = 0;           // row length h_Gc was allocated for (0: none)
 };
+constexpr int NLANES = 3;
 
 struct tolcuda_ctx {
     tolcuda_config cfg;
@@ -56,7 +62,10 @@ struct tolcuda_ctx {
     double *d_one = nullptr;  // same layout on the device
     long ox = 0, oF = 0, oG = 0;
     // host-pointer batch path
-    BatchLane lane[2];
+    BatchLane lane[NLANES];
+    int compact_host = 1;  // host-pointer path: compact G across PCIe, expanded by host threads (TOLCUDA_COMPACT=0: full rows)
+    int host_threads = 0;  // 0: HostPool::default_threads()
+    std::unique_ptr<HostPool> pool;
     long launches = 0;
     double *d_grid = nullptr;  // wind cube: gx | gy | gz | v
 };
@@ -69,9 +78,10 @@ tolcuda_ctx *g_bound = nullptr;
 long round_up(long v, long m) { return (v + m - 1) / m * m; }
 
 int launch(tolcuda_ctx *h, cudaStream_t st, int B, const double *x, long ldx, double *F, long ldF,
-           double *G, long ldG, int needF, int needG, double *S = nullptr, long ldS = 0) {
-    FgLaunch L;
+           double *G, long ldG, int needF, int needG, double *S = nullptr, long ldS = 0, int compact = 0) {
+    FgLaunch L{};
     L.S = S, L.ldS = ldS;
+    L.compact = compact;
     L.c = &h->c;
     L.B = B;
     L.x = x, L.ldx = ldx, L.F = F, L.ldF = ldF, L.G = G, L.ldG = ldG;
@@ -90,26 +100,40 @@ void free_lane(BatchLane &l) {
     if (l.d_F) cudaFree(l.d_F);
     if (l.d_G) cudaFree(l.d_G);
     if (l.d_S) cudaFree(l.d_S);
+    if (l.h_Gc) cudaFreeHost(l.h_Gc);
+    if (l.done) cudaEventDestroy(l.done);
     if (l.stream) cudaStreamDestroy(l.stream);
     l = BatchLane();
 }
 
-int ensure_lane(tolcuda_ctx *h, BatchLane &l, int cap) {
+// device buffers for `cap` trajectories with G rows of ldG doubles; ldGc > 0: plus the pinned landing area
+int ensure_lane(tolcuda_ctx *h, BatchLane &l, int cap, long ldG, long ldGc) {
     if (!l.stream) CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
-    if (l.cap >= cap) return 0;
-    if (l.d_x) cudaFree(l.d_x);
-    if (l.d_F) cudaFree(l.d_F);
-    if (l.d_G) cudaFree(l.d_G);
-    if (l.d_S) cudaFree(l.d_S);
-    l.d_x = l.d_F = l.d_G = l.d_S = nullptr;
-    l.cap = 0;
-    const long ldx = tolcuda_padded_ld(h->c.n), ldF = tolcuda_padded_ld(h->c.neF),
-               ldG = tolcuda_padded_ld(h->c.neG);
-    CU(cudaMalloc(&l.d_x, sizeof(double) * ldx * cap));
-    CU(cudaMalloc(&l.d_F, sizeof(double) * ldF * cap));
-    CU(cudaMalloc(&l.d_G, sizeof(double) * ldG * cap));
-    CU(cudaMalloc(&l.d_S, sizeof(double) * 4 * cap));
-    l.cap = cap;
+    if (!l.done) CU(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+    if (l.cap < cap || l.ldG < ldG) {
+        if (l.d_x) cudaFree(l.d_x);
+        if (l.d_F) cudaFree(l.d_F);
+        if (l.d_G) cudaFree(l.d_G);
+        if (l.d_S) cudaFree(l.d_S);
+        l.d_x = l.d_F = l.d_G = l.d_S = nullptr;
+        const int ncap = std::max(cap, l.cap);
+        const long nldG = std::max(ldG, l.ldG);
+        l.cap = 0, l.ldG = 0;
+        const long ldx = tolcuda_padded_ld(h->c.n), ldF = tolcuda_padded_ld(h->c.neF);
+        CU(cudaMalloc(&l.d_x, sizeof(double) * ldx * ncap));
+        CU(cudaMalloc(&l.d_F, sizeof(double) * ldF * ncap));
+        CU(cudaMalloc(&l.d_G, sizeof(double) * nldG * ncap));
+        CU(cudaMalloc(&l.d_S, sizeof(double) * 4 * ncap));
+        if (l.h_Gc) cudaFreeHost(l.h_Gc);  // sized with cap
+        l.h_Gc = nullptr, l.ldGc = 0;
+        l.cap = ncap, l.ldG = nldG;
+    }
+    if (ldGc > 0 && l.ldGc < ldGc) {
+        if (l.h_Gc) cudaFreeHost(l.h_Gc);
+        l.h_Gc = nullptr, l.ldGc = 0;
+        CU(cudaMallocHost(&l.h_Gc, sizeof(double) * ldGc * l.cap));
+        l.ldGc = ldGc;
+    }
     return 0;
 }
 
@@ -208,6 +232,7 @@ int tolcuda_create(const tolcuda_config *cfg, tolcuda_handle *out) {
 
     if (const char *env = std::getenv("TOLCUDA_KERNEL")) h->kernel = std::atoi(env);  // tests / tuning
     if (const char *env = std::getenv("TOLCUDA_ZEROCOPY")) h->zero_copy = std::atoi(env);
+    if (const char *env = std::getenv("TOLCUDA_COMPACT")) h->compact_host = std::atoi(env);
 
     int rc = 0;
     do {
@@ -310,8 +335,10 @@ int tolcuda_destroy(tolcuda_handle h) {
     }
     cudaSetDevice(h->cfg.device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
-    free_lane(h->lane[0]);
-    free_lane(h->lane[1]);
+    for (BatchLane &l : h->lane) {
+        if (l.stream) cudaStreamSynchronize(l.stream);
+        free_lane(l);
+    }
     if (h->h_one) cudaFreeHost(h->h_one);
     if (h->d_one) cudaFree(h->d_one);
     if (h->d_grid) cudaFree(h->d_grid);
@@ -434,11 +461,18 @@ int tolcuda_eval_batch_summary(tolcuda_handle h, int B, const double *x, long ld
                                double *G, long ldG, double *summary, long lds, int flags) {
     if (!h || B < 0 || (summary && lds < 4)) return TOLCUDA_EINVAL;
     const int needF = (flags & TOLCUDA_NEED_F) != 0;
-    // bits 8.. of flags: kernel experiment switches (undocumented, tools/kbench.py only)
-    const int needG = (flags & TOLCUDA_NEED_G) ? (1 | (((flags >> 8) & 0xff) << 1)) : 0;
+    // bits 16.. of flags: kernel experiment switches (undocumented, tools/kbench.py only)
+    const int needG = (flags & TOLCUDA_NEED_G) ? (1 | (((flags >> 16) & 0xff) << 1)) : 0;
     if (B == 0 || (!needF && !needG && !summary)) return 0;
     const FgConst &c = h->c;
-    if (!x || ldx < c.n || (needF && (!F || ldF < c.neF)) || (needG && (!G || ldG < c.neG))) {
+    const long lenGc = compact_len(c.form, c.ts);
+    const bool compact_rows = (flags & TOLCUDA_COMPACT_G) != 0;  // the CALLER's G holds compact rows
+    if (compact_rows && summary) {
+        set_error("tolcuda_eval_batch_summary: TOLCUDA_COMPACT_G cannot be combined with a summary");
+        return TOLCUDA_EUNSUPPORTED;
+    }
+    if (!x || ldx < c.n || (needF && (!F || ldF < c.neF)) ||
+        (needG && (!G || ldG < (compact_rows ? lenGc : (long)c.neG)))) {
         set_error("tolcuda_eval_batch: null pointer or leading dimension shorter than the row");
         return TOLCUDA_EINVAL;
     }
@@ -455,15 +489,23 @@ int tolcuda_eval_batch_summary(tolcuda_handle h, int B, const double *x, long ld
         }
     }
     if (!host) {
-        int rc = launch(h, h->stream, B, x, ldx, F, ldF, G, ldG, needF, needG, summary, lds);
+        int rc = launch(h, h->stream, B, x, ldx, F, ldF, G, ldG, needF, needG, summary, lds, compact_rows);
         if (rc) return rc;
         if (!(flags & TOLCUDA_NO_SYNC)) CU(cudaStreamSynchronize(h->stream));
         return 0;
     }
 
-    // Host pointers: chunks of trajectories alternate between two lanes; each lane's stream carries
-    // H2D(x) -> kernel -> D2H(F, G) for its chunk, so one lane's copies overlap the other's kernel.
-    const long dldx = tolcuda_padded_ld(c.n), dldF = tolcuda_padded_ld(c.neF), dldG = tolcuda_padded_ld(c.neG);
+    // Host pointers: chunks of trajectories rotate over NLANES lanes; a lane's stream carries
+    // H2D(x) -> kernel -> D2H(F, G) for its chunk, so one lane's copies overlap another's kernel.
+    // G normally crosses PCIe as compact rows (31 of a window's 104 values, compact.cpp) into the lane's
+    // pinned landing area and is expanded from there into the caller's G by the host thread pool while
+    // the next lanes are in flight; TOLCUDA_FULL_G_COPY (or TOLCUDA_COMPACT=0, or a summary request)
+    // copies full rows straight into the caller's G instead.
+    const bool via_compact = needG && !compact_rows && !summary && h->compact_host && !(flags & TOLCUDA_FULL_G_COPY);
+    const bool dev_compact = via_compact || compact_rows;  // layout of the lane's d_G
+    const long dldx = tolcuda_padded_ld(c.n), dldF = tolcuda_padded_ld(c.neF);
+    const long dldG = tolcuda_padded_ld(dev_compact ? lenGc : (long)c.neG);
+    const long rowG = dev_compact ? lenGc : (long)c.neG;  // doubles of a G row that cross PCIe
     const size_t per_traj = sizeof(double) * (size_t)(dldx + dldF + dldG);
     size_t budget = (size_t)256 << 20;  // device bytes per lane
     if (const char *env = std::getenv("TOLCUDA_CHUNK_MB")) {
@@ -472,20 +514,23 @@ int tolcuda_eval_batch_summary(tolcuda_handle h, int B, const double *x, long ld
     }
     int chunk = (int)std::max<size_t>(1, budget / per_traj);
     chunk = std::min(chunk, B);
-    if (B > chunk && B < 2 * chunk) chunk = (B + 1) / 2;
-    for (int l = 0; l < 2; l++) {
-        if (l == 1 && B <= chunk) break;
-        int rc = ensure_lane(h, h->lane[l], chunk);
+    if (B > chunk && B < NLANES * chunk) chunk = (B + NLANES - 1) / NLANES;
+    const int nchunks = (B + chunk - 1) / chunk;
+    const int nlanes = std::min(NLANES, nchunks);
+    for (int l = 0; l < nlanes; l++) {
+        int rc = ensure_lane(h, h->lane[l], chunk, dldG, via_compact ? dldG : 0);
         if (rc) return rc;
     }
-    int li = 0;
-    for (int b0 = 0; b0 < B; b0 += chunk, li ^= 1) {
-        BatchLane &l = h->lane[li];
-        const int nb = std::min(chunk, B - b0);
+    if (via_compact && !h->pool)
+        h->pool.reset(new HostPool(h->host_threads > 0 ? h->host_threads : HostPool::default_threads()));
+
+    auto enqueue = [&](int ci) -> int {
+        BatchLane &l = h->lane[ci % NLANES];
+        const int b0 = ci * chunk, nb = std::min(chunk, B - b0);
         CU(cudaMemcpy2DAsync(l.d_x, sizeof(double) * dldx, x + (size_t)b0 * ldx, sizeof(double) * ldx,
                              sizeof(double) * c.n, nb, cudaMemcpyHostToDevice, l.stream));
         int rc = launch(h, l.stream, nb, l.d_x, dldx, l.d_F, dldF, l.d_G, dldG, needF, needG,
-                        summary ? l.d_S : nullptr, 4);
+                        summary ? l.d_S : nullptr, 4, dev_compact);
         if (rc) return rc;
         if (needF)
             CU(cudaMemcpy2DAsync(F + (size_t)b0 * ldF, sizeof(double) * ldF, l.d_F, sizeof(double) * dldF,
@@ -493,12 +538,59 @@ int tolcuda_eval_batch_summary(tolcuda_handle h, int B, const double *x, long ld
         if (summary)
             CU(cudaMemcpy2DAsync(summary + (size_t)b0 * lds, sizeof(double) * lds, l.d_S, sizeof(double) * 4,
                                  sizeof(double) * 4, nb, cudaMemcpyDeviceToHost, l.stream));
-        if (needG)
+        if (needG && via_compact)
+            CU(cudaMemcpyAsync(l.h_Gc, l.d_G, sizeof(double) * dldG * nb, cudaMemcpyDeviceToHost, l.stream));
+        else if (needG)
             CU(cudaMemcpy2DAsync(G + (size_t)b0 * ldG, sizeof(double) * ldG, l.d_G, sizeof(double) * dldG,
-                                 sizeof(double) * c.neG, nb, cudaMemcpyDeviceToHost, l.stream));
+                                 sizeof(double) * rowG, nb, cudaMemcpyDeviceToHost, l.stream));
+        CU(cudaEventRecord(l.done, l.stream));
+        return 0;
+    };
+    auto drain = [&]() {  // error exit: nothing of this call may still be writing into the caller's arrays
+        for (int l = 0; l < nlanes; l++) cudaStreamSynchronize(h->lane[l].stream);
+    };
+    int rc = 0;
+    for (int ci = 0; ci < nlanes && !rc; ci++) rc = enqueue(ci);
+    for (int ci = 0; ci < nchunks && !rc; ci++) {
+        BatchLane &l = h->lane[ci % NLANES];
+        cudaError_t e = cudaEventSynchronize(l.done);
+        if (e != cudaSuccess) {
+            rc = cuda_fail(e, "cudaEventSynchronize");
+            break;
+        }
+        if (via_compact) {
+            const int b0 = ci * chunk, nb = std::min(chunk, B - b0);
+            expand_rows(*h->pool, c.form, c.ts, nb, l.h_Gc, dldG, G + (size_t)b0 * ldG, ldG);
+        }
+        if (ci + NLANES < nchunks) rc = enqueue(ci + NLANES);
     }
-    CU(cudaStreamSynchronize(h->lane[0].stream));
-    if (h->lane[1].stream) CU(cudaStreamSynchronize(h->lane[1].stream));
+    if (rc) drain();
+    return rc;
+}
+
+long tolcuda_compact_len(int formulation, int ts) {
+    if ((formulation != TOLCUDA_G7 && formulation != TOLCUDA_S10) || ts < 1) return TOLCUDA_EINVAL;
+    return compact_len(formulation, ts);
+}
+
+int tolcuda_expand_compact_g(int formulation, int ts, long B, const double *Gc, long ldGc, double *G, long ldG,
+                             int threads) {
+    if ((formulation != TOLCUDA_G7 && formulation != TOLCUDA_S10) || ts < 1 || B < 0) return TOLCUDA_EINVAL;
+    int neG;
+    pattern_dims(formulation, ts, nullptr, nullptr, &neG, nullptr, nullptr);
+    if (B > 0 && (!Gc || !G || ldGc < compact_len(formulation, ts) || ldG < neG)) {
+        set_error("tolcuda_expand_compact_g: null pointer or leading dimension shorter than the row");
+        return TOLCUDA_EINVAL;
+    }
+    HostPool pool(threads > 0 ? threads : HostPool::default_threads());
+    expand_rows(pool, formulation, ts, B, Gc, ldGc, G, ldG);
+    return 0;
+}
+
+int tolcuda_set_host_threads(tolcuda_handle h, int threads) {
+    if (!h || threads < 0) return TOLCUDA_EINVAL;
+    h->host_threads = threads;
+    h->pool.reset();  // rebuilt with the new size by the next host-pointer batch call
     return 0;
 }
 

@@ -3,6 +3,7 @@
 #define TOLCUDA_INTERNAL_H_
 
 #include <cmath>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -23,6 +24,30 @@ void pattern_build(int form, int ts, std::vector<int> &iG, std::vector<int> &jG)
 
 void initial_guess(const tolcuda_config &cfg, double *x);
 void bounds(const tolcuda_config &cfg, double *xlow, double *xupp, double *Flow, double *Fupp);
+
+// compact G rows (compact.cpp): length of a row, expansion of one row / of B rows on a host thread pool
+long compact_len(int form, int ts);
+void expand_row(int form, int ts, const double *src, double *dst);
+
+class HostPool {
+public:
+    explicit HostPool(int threads);
+    ~HostPool();
+    HostPool(const HostPool &) = delete;
+    HostPool &operator=(const HostPool &) = delete;
+    int threads() const { return threads_; }
+    // fn(i) for i in [0, n) on the pool's threads and the caller's; returns when all are done
+    void parallel_for(long n, const std::function<void(long)> &fn);
+    // TOLCUDA_HOST_THREADS, else the cores this process may run on divided by LOCAL_WORLD_SIZE
+    static int default_threads();
+
+private:
+    struct Impl;
+    Impl *impl_;
+    int threads_;
+};
+
+void expand_rows(HostPool &pool, int form, int ts, long B, const double *Gc, long ldGc, double *G, long ldG);
 
 int read_params(const std::string &path, std::vector<double> &out);
 int read_aircraft(const std::string &root, const std::string &name, double ac[15]);

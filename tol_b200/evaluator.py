@@ -9,7 +9,7 @@ from . import lib as _l
 
 G7, S10 = 7, 10
 NEED_F, NEED_G = 0x1, 0x2
-HOST_PTRS, DEVICE_PTRS, NO_SYNC = 0x10, 0x20, 0x40
+HOST_PTRS, DEVICE_PTRS, NO_SYNC, COMPACT_G, FULL_G_COPY = 0x10, 0x20, 0x40, 0x80, 0x100
 _FORM = {"G7": G7, "S10": S10, G7: G7, S10: S10}
 
 
@@ -73,6 +73,25 @@ def padded_ld(n):
     return int(_l.load().tolcuda_padded_ld(int(n)))
 
 
+def compact_len(mission, ts):
+    """doubles of a compact G row (tolcuda_compact_len)"""
+    v = int(_l.load().tolcuda_compact_len(_FORM[mission], int(ts)))
+    _l.check(min(v, 0))
+    return v
+
+
+def expand_compact_g(mission, ts, Gc, G=None, threads=0):
+    """tolcuda_expand_compact_g: compact rows [B, >= compact_len] -> rows in coordinate order (host only)"""
+    _, _, neG = problem_dims(mission, ts)
+    B = Gc.shape[0]
+    assert Gc.dtype == np.float64 and (B == 0 or Gc.strides[1] == 8)
+    if G is None:
+        G = np.empty((B, neG))
+    _l.check(_l.load().tolcuda_expand_compact_g(_FORM[mission], int(ts), B, Gc.ctypes.data, Gc.strides[0] // 8,
+                                                G.ctypes.data, G.strides[0] // 8, int(threads)))
+    return G
+
+
 class Evaluator:
     def __init__(self, mission, ts, aircraft, gains, goal_ned, wind_model=1, device=0):
         L = _l.load()
@@ -107,6 +126,21 @@ class Evaluator:
         n, neF, neG = C.c_int(), C.c_int(), C.c_int()
         _l.check(L.tolcuda_dims(self.h, C.byref(n), C.byref(neF), C.byref(neG)))
         self.n, self.neF, self.neG = n.value, neF.value, neG.value
+        self.compact_len = int(L.tolcuda_compact_len(self.cfg_form(), self.cfg_ts()))
+
+    def _config(self):
+        cfg = _l.Config()
+        _l.check(self.L.tolcuda_get_config(self.h, C.byref(cfg)))
+        return cfg
+
+    def cfg_form(self):
+        return self._config().formulation
+
+    def cfg_ts(self):
+        return self._config().ts
+
+    def set_host_threads(self, threads):
+        _l.check(self.L.tolcuda_set_host_threads(self.h, int(threads)))
 
     def close(self):
         if getattr(self, "h", None):
@@ -150,24 +184,27 @@ class Evaluator:
                              C.byref(leniu), None, C.byref(lenru))
         return st.value, F, G
 
-    def eval_batch_host(self, X, F=None, G=None, needF=True, needG=True):
-        """tolcuda_eval_batch with HOST arrays (numpy, or pinned torch tensors via .numpy())"""
+    def eval_batch_host(self, X, F=None, G=None, needF=True, needG=True, full_copy=False, compact_rows=False):
+        """tolcuda_eval_batch with HOST arrays (numpy, or pinned torch tensors via .numpy());
+        full_copy: TOLCUDA_FULL_G_COPY; compact_rows: G receives compact rows (TOLCUDA_COMPACT_G)"""
         B = X.shape[0]
         assert X.dtype == np.float64 and X.strides[1] == 8
         if F is None:
             F = np.empty((B, self.neF))
         if G is None:
-            G = np.empty((B, self.neG))
+            G = np.empty((B, self.compact_len if compact_rows else self.neG))
         flags = (NEED_F if needF else 0) | (NEED_G if needG else 0) | HOST_PTRS
+        flags |= (FULL_G_COPY if full_copy else 0) | (COMPACT_G if compact_rows else 0)
         _l.check(self.L.tolcuda_eval_batch(self.h, B, X.ctypes.data, X.strides[0] // 8, F.ctypes.data,
                                            F.strides[0] // 8, G.ctypes.data, G.strides[0] // 8, flags))
         return F, G
 
-    def eval_batch_device(self, X, F, G, needF=True, needG=True, sync=True):
+    def eval_batch_device(self, X, F, G, needF=True, needG=True, sync=True, compact_rows=False):
         """tolcuda_eval_batch with torch CUDA tensors [B, ld] (float64, row-contiguous)"""
         B = X.shape[0]
         flags = (NEED_F if needF else 0) | (NEED_G if needG else 0) | DEVICE_PTRS | (0 if sync else NO_SYNC)
-        flags |= (int(needG) >> 1) << 8  # experiment switches (tools/kbench.py)
+        flags |= COMPACT_G if compact_rows else 0
+        flags |= (int(needG) >> 1) << 16  # experiment switches (tools/kbench.py)
         _l.check(self.L.tolcuda_eval_batch(self.h, B, X.data_ptr(), X.stride(0), F.data_ptr(), F.stride(0),
                                            G.data_ptr(), G.stride(0), flags))
 
