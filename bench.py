@@ -305,7 +305,7 @@ def run_ours(args, wl_name):
     del Fd, Gd
     torch.cuda.empty_cache()
     ev.use_own_stream()
-    host_threads = max(1, len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
+    host_threads = max(1, min(8, len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))))
     ev.set_host_threads(host_threads)
     Fh = torch.empty(B, ldF, dtype=torch.float64, pin_memory=True)
     Gh = torch.empty(B, ldG, dtype=torch.float64, pin_memory=True)

@@ -135,11 +135,15 @@ def _varying_positions():
 
 
 @pytest.mark.parametrize("name", GOLDEN)
-@pytest.mark.parametrize("shift", [0, 1])
-def test_compact_rows_expand_to_reference_rows(name, shift):
+@pytest.mark.parametrize("shift", range(8))
+@pytest.mark.parametrize("wide", [True, False])
+def test_compact_rows_expand_to_reference_rows(name, shift, wide, monkeypatch):
     """tolcuda_expand_compact_g (the host half of the host-pointer batch path): compact rows cut out of the
-    REFERENCE's G expand back to the reference's G exactly, constants included; shift=1 puts the
-    destination rows 8 bytes off 16-byte alignment (the other store path)"""
+    REFERENCE's G expand back to the reference's G exactly, constants included; `shift` moves the
+    destination rows through all eight 8-byte phases of a cache line (every instantiation of the AVX-512
+    line path, both alignments of the SSE2 path)"""
+    if not wide:
+        monkeypatch.setenv("TOLCUDA_NO_AVX512", "1")
     g = load_golden(name)
     m, ts, neG = str(g["mission"]), int(g["ts"]), int(g["neG"])
     nbG = 42 if m == "G7" else 33
@@ -159,7 +163,7 @@ def test_compact_rows_expand_to_reference_rows(name, shift):
     Gc[:, R0:R0 + 31 * ts] = G[:, R0:R0 + 104 * ts].reshape(B, ts, 104)[:, :, pos].reshape(B, -1)
     Gc[:, R0 + 31 * ts:R0 + 31 * ts + nbG] = G[:, neG - nbG:]
     Gc[:, R0 + 31 * ts + nbG] = -g["x"][:, 0]
-    buf = np.full((B, neG + 4), np.nan)
+    buf = np.full((B, neG + 8 + (-neG) % 8), np.nan)  # rows a multiple of 64 bytes: same phase in every row
     out = buf[:, shift:shift + neG]
     T.evaluator.expand_compact_g(m, ts, Gc, out, threads=3)
     assert np.array_equal(out, G)

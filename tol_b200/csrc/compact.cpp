@@ -17,7 +17,7 @@
 //
 // Writes are non-temporal (the destination, 11 GB per 65,536-trajectory step, is not read back by this
 // library), spread over a small pool of host threads by trajectory.
-#include <emmintrin.h>
+#include <immintrin.h>
 #include <sched.h>
 
 #include <atomic>
@@ -93,6 +93,90 @@ inline void nt_copy(double *dst, const double *src, long cnt) {
     if (i < cnt) nt1(dst + i, src[i]);
 }
 
+// ---- AVX-512 path ---------------------------------------------------------------------------------------
+//
+// The record region of a row is a periodic stream: output double j (counted from the first record) holds
+// record position j mod 104, and 104 doubles are exactly 13 cache lines.  Starting at the first 64-byte
+// aligned address inside the region (Q doubles in), line l of every 13-line period therefore has a fixed
+// 8-lane layout: which lanes take the next values of the compact stream (mask) and which constants sit in
+// the others (template).  One masked expand-load (the next popcount(mask) compact values into the masked
+// lanes, the template elsewhere) and one streaming 64-byte store produce a line.
+struct LineTab {
+    uint8_t var[13];   // lanes fed from the compact stream
+    uint8_t mdt[13];   // lanes holding -dt
+    double tmpl[13][8];  // constants (0 in the var and -dt lanes)
+    int8_t cnt[13];    // popcount(var)
+};
+constexpr LineTab make_lines(int q) {
+    LineTab t{};
+    for (int l = 0; l < 13; l++) {
+        for (int e = 0; e < 8; e++) {
+            const int m = kMap.m[(q + 8 * l + e) % REC];
+            if (m >= 0) t.var[l] |= (uint8_t)(1u << e), t.cnt[l]++;
+            else if (m == -4) t.mdt[l] |= (uint8_t)(1u << e);
+            t.tmpl[l][e] = m == -2 ? 1.0 : (m == -3 ? -1.0 : 0.0);
+        }
+    }
+    return t;
+}
+template <int Q>
+struct Lines {
+    static constexpr LineTab tab = make_lines(Q);
+};
+
+inline double rec_val_rt(int pos, const double *&v, const double mdt) {
+    const int m = kMap.m[pos];
+    if (m >= 0) return *v++;
+    return m == -1 ? 0.0 : (m == -2 ? 1.0 : (m == -3 ? -1.0 : mdt));
+}
+
+// records of one row: dst = first record (8-byte aligned, Q doubles before the next 64-byte boundary),
+// v = the row's compact window values
+template <int Q>
+__attribute__((target("avx512f"))) void records_avx512(double *dst, const double *v, const double mdt, const int ts) {
+    constexpr const LineTab &T = Lines<Q>::tab;
+    const long total = (long)REC * ts;
+    long j = 0;
+    for (; j < Q && j < total; j++) nt1(dst + j, rec_val_rt((int)(j % REC), v, mdt));
+    if (j == total) return;
+    __m512d tm[13];
+    const __m512d vm = _mm512_set1_pd(mdt);
+#pragma GCC unroll 13
+    for (int l = 0; l < 13; l++) tm[l] = _mm512_mask_blend_pd((__mmask8)T.mdt[l], _mm512_loadu_pd(T.tmpl[l]), vm);
+    double *out = dst + Q;
+    const long nlines = (total - Q) / 8;
+    long i = 0;
+    for (; i + 13 <= nlines; i += 13) {
+#pragma GCC unroll 13
+        for (int l = 0; l < 13; l++) {
+            _mm512_stream_pd(out + 8 * l, _mm512_mask_expandloadu_pd(tm[l], (__mmask8)T.var[l], v));
+            v += T.cnt[l];
+        }
+        out += REC;
+    }
+    for (int l = 0; i < nlines; i++, l++, out += 8) {
+        _mm512_stream_pd(out, _mm512_mask_expandloadu_pd(tm[l], (__mmask8)T.var[l], v));
+        v += T.cnt[l];
+    }
+    for (j = Q + 8 * nlines; j < total; j++) nt1(dst + j, rec_val_rt((int)(j % REC), v, mdt));
+}
+
+// AVX-512 available and not switched off (TOLCUDA_NO_AVX512, for tests of the SSE2 path)
+bool have_avx512() { return __builtin_cpu_supports("avx512f") && !std::getenv("TOLCUDA_NO_AVX512"); }
+
+void records_dispatch_avx512(double *dst, const double *v, const double mdt, const int ts) {
+    switch ((8 - (int)((reinterpret_cast<uintptr_t>(dst) >> 3) & 7)) & 7) {
+        case 0: return records_avx512<0>(dst, v, mdt, ts);
+        case 1: return records_avx512<1>(dst, v, mdt, ts);
+        case 2: return records_avx512<2>(dst, v, mdt, ts);
+        case 3: return records_avx512<3>(dst, v, mdt, ts);
+        case 4: return records_avx512<4>(dst, v, mdt, ts);
+        case 5: return records_avx512<5>(dst, v, mdt, ts);
+        case 6: return records_avx512<6>(dst, v, mdt, ts);
+        default: return records_avx512<7>(dst, v, mdt, ts);
+    }
+}
+
 }  // namespace
 
 long compact_len(int form, int ts) {
@@ -101,7 +185,9 @@ long compact_len(int form, int ts) {
     return (long)R0 + (long)NVAR * ts + nbG + 1;
 }
 
-void expand_row(int form, int ts, const double *src, double *dst) {
+void expand_row(int form, int ts, const double *src, double *dst) { expand_row(form, ts, src, dst, have_avx512()); }
+
+void expand_row(int form, int ts, const double *src, double *dst, bool wide) {
     int R0, nbG;
     pattern_dims(form, ts, nullptr, nullptr, nullptr, &R0, &nbG);
     const double *bsrc = src + R0 + (long)NVAR * ts;
@@ -109,7 +195,10 @@ void expand_row(int form, int ts, const double *src, double *dst) {
     nt_copy(dst, src, R0);
     double *rec = dst + R0;
     const double *v = src + R0;
-    if ((reinterpret_cast<uintptr_t>(rec) & 15) == 0) {
+    if (wide) {
+        records_dispatch_avx512(rec, v, mdt, ts);
+        rec += (long)REC * ts;
+    } else if ((reinterpret_cast<uintptr_t>(rec) & 15) == 0) {
         for (int k = 0; k < ts; k++, rec += REC, v += NVAR)
             record_aligned(rec, v, mdt, std::make_integer_sequence<int, REC / 2>());
     } else {
@@ -169,7 +258,8 @@ int HostPool::default_threads() {
         const int w = std::atoi(env);
         if (w > 1) cores = std::max(1, cores / w);
     }
-    return std::min(cores, 64);
+    // the expansion is bound by host memory bandwidth: 8 threads reach it on the B200 host (tools/expandbw.py)
+    return std::min(cores, 8);
 }
 
 HostPool::HostPool(int threads) : impl_(new Impl), threads_(std::max(1, threads)) {
@@ -206,9 +296,10 @@ void HostPool::parallel_for(long n, const std::function<void(long)> &fn) {
 
 void expand_rows(HostPool &pool, int form, int ts, long B, const double *Gc, long ldGc, double *G, long ldG) {
     constexpr long BLK = 4;  // trajectories per work item
+    const bool wide = have_avx512();
     const std::function<void(long)> job = [&](long item) {
         const long b1 = std::min(B, (item + 1) * BLK);
-        for (long b = item * BLK; b < b1; b++) expand_row(form, ts, Gc + b * ldGc, G + b * ldG);
+        for (long b = item * BLK; b < b1; b++) expand_row(form, ts, Gc + b * ldGc, G + b * ldG, wide);
         _mm_sfence();  // streaming stores are weakly ordered: make them visible before the item counts as done
     };
     pool.parallel_for((B + BLK - 1) / BLK, job);

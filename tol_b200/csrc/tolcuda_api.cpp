@@ -507,7 +507,7 @@ int tolcuda_eval_batch_summary(tolcuda_handle h, int B, const double *x, long ld
     const long dldG = tolcuda_padded_ld(dev_compact ? lenGc : (long)c.neG);
     const long rowG = dev_compact ? lenGc : (long)c.neG;  // doubles of a G row that cross PCIe
     const size_t per_traj = sizeof(double) * (size_t)(dldx + dldF + dldG);
-    size_t budget = (size_t)256 << 20;  // device bytes per lane
+    size_t budget = (size_t)32 << 20;  // device bytes per lane (measured: 8..64 MB equally good, tools/expandbw.py)
     if (const char *env = std::getenv("TOLCUDA_CHUNK_MB")) {
         long mb = std::atol(env);
         if (mb > 0) budget = (size_t)mb << 20;

@@ -28,6 +28,7 @@ void bounds(const tolcuda_config &cfg, double *xlow, double *xupp, double *Flow,
 // compact G rows (compact.cpp): length of a row, expansion of one row / of B rows on a host thread pool
 long compact_len(int form, int ts);
 void expand_row(int form, int ts, const double *src, double *dst);
+void expand_row(int form, int ts, const double *src, double *dst, bool wide);  // wide: AVX-512 line stores
 
 class HostPool {
 public:

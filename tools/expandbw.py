@@ -20,7 +20,7 @@ n, neF, neG = T.problem_dims(m, ts)
 Lc = compact_len(m, ts)
 Gc = torch.randn(B, padded_ld(Lc), dtype=torch.float64).pin_memory()
 G = torch.empty(B, padded_ld(neG), dtype=torch.float64).pin_memory()
-for th in (1, 2, 4, 8, 12, 16):
+for th in (1, 4, 16):
     expand_compact_g(m, ts, Gc.numpy(), G.numpy(), threads=th)
     t0 = time.perf_counter()
     for _ in range(3):
@@ -33,9 +33,9 @@ ev = T.Evaluator.from_golden(g)
 X = torch.zeros(B, padded_ld(n), dtype=torch.float64).pin_memory()
 T.synth.batch(g["x"][0], T.synth.SEED_S10, 0, B, out=X.numpy())
 F = torch.empty(B, padded_ld(neF), dtype=torch.float64).pin_memory()
-for mb in (32, 64, 128, 256, 512):
+for mb in (1, 2, 4, 8, 16, 32, 64):
     os.environ["TOLCUDA_CHUNK_MB"] = str(mb)
-    for th in (8, 16):
+    for th in (4, 8, 16):
         ev.set_host_threads(th)
         for full in (False,):
             ev.eval_batch_host(X.numpy(), F.numpy(), G.numpy(), full_copy=full)
