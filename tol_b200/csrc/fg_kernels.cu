@@ -48,10 +48,29 @@ namespace {
 constexpr int PX = TOLCUDA_PX;
 constexpr int PF = TOLCUDA_PF;
 constexpr int REC = TOLCUDA_REC;
-constexpr int NPP = 4;                 // windows drained per group: one dense buffer of NPP records
-constexpr int NBUF = 2;                // record buffers per warp (the TMA unit reads one while lanes fill the other)
-constexpr int SX_LEN = 368;            // a warp's x slice: slot for x[11*k0] + 33 nodes = 364 doubles
-constexpr int TILE_LEN = NBUF * NPP * REC;  // 832 doubles
+// Record buffers.  A drain pass hands NPP windows (lanes NPP*g .. NPP*g+NPP-1) to the TMA unit: each of those
+// lanes places its 33 x-dependent values in its own record slot (the slots' constants are written once per
+// warp), then lane 0 issues the bulk copies, one per dense run of UNIT records.  The layout is a build-time
+// choice so that variants can be measured side by side (tools/exp/build_variant.sh); measured on B200, S10
+// ts=200, B=16,384 (profiles/r1_history.md): NPP=4 / 2 buffers / dense quads 0.558 ms; the same with padded
+// pairs (conflict-free stores, two copies per pass) 0.589; NPP=16 / 1 buffer / padded pairs 0.634;
+// NPP=16 dense 0.584; NPP=8 / 1 buffer / padded pairs 0.584.  A kernel that only moves the same bytes
+// (tools/exp/storebw.cu: x row in, F row out, G row out as 3,328-byte bulk copies, no arithmetic) takes 0.50.
+#ifndef TOLCUDA_NPP
+#define TOLCUDA_NPP 4
+#define TOLCUDA_NBUF 2
+#define TOLCUDA_UNIT 4
+#define TOLCUDA_PADW 0
+#endif
+constexpr int NPP = TOLCUDA_NPP;       // windows per drain pass
+constexpr int NBUF = TOLCUDA_NBUF;     // record buffers per warp (2: the TMA unit reads one while lanes fill the other)
+constexpr int UNIT = TOLCUDA_UNIT;     // records per dense run = per bulk copy
+constexpr int PADW = TOLCUDA_PADW;     // doubles between runs (even: runs stay 16-byte aligned)
+constexpr int USTR = UNIT * REC + PADW;                     // run stride
+constexpr int BUF_LEN = (NPP / UNIT) * USTR;
+constexpr int TILE_LEN = NBUF * BUF_LEN;
+constexpr int SX_LEN = 368;            // a warp's x slice: slot for x[11*k0] + 33 nodes = 364 doubles (tile stays 128-byte aligned)
+static_assert(NPP % UNIT == 0 && 32 % NPP == 0 && PADW % 2 == 0 && NBUF * NPP <= 32, "record buffer layout");
 constexpr int WARP_SMEM = SX_LEN + TILE_LEN;        // kernel A
 constexpr int WARP_SMEM_B = 2 * SX_LEN + TILE_LEN;  // kernel B: double-buffered x slice
 constexpr int F_LD = 10;               // smem stride of a window's 8 defects (== 2 mod 4)
@@ -118,11 +137,15 @@ __device__ __forceinline__ void slice_prefetch(double *sx, const double *xs, con
 
 // TMA bulk copy shared -> global of `bytes` (a multiple of 16; both sides 16-byte aligned), as its own
 // bulk group of the calling thread
-__device__ __forceinline__ void bulk_store(double *gdst, const double *ssrc, const int bytes) {
+__device__ __forceinline__ void bulk_issue(double *gdst, const double *ssrc, const int bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
                  "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
                  : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(double *gdst, const double *ssrc, const int bytes) {
+    bulk_issue(gdst, ssrc, bytes);
+    bulk_commit();
 }
 // wait until all but the newest N bulk groups of the calling thread have finished READING shared memory
 template <int N>
@@ -135,7 +158,12 @@ __device__ __forceinline__ void bulk_wait_read() {
 // Record layout (row s of the window at 13*s: [d/d dt, d/d c0..c10 @k, d/d c_s @k+1]).  Structural
 // constants: tabG zero-initialisation and the +-1 entries (src/problem.cpp:1038, 1084, 1098, 1112, 1170,
 // 1182, 1204); everything x-dependent is zeroed here and written per window by record_store.
-__device__ __forceinline__ void record_init(double *rec) {
+// offset of record slot q (0 .. NPP-1) within a record buffer
+__device__ __forceinline__ int slot_offset(const int q) { return (q / UNIT) * USTR + (q % UNIT) * REC; }
+// lanes 0 .. NBUF*NPP-1 each prepare one record slot: zeros, then the 13 structural +-1 entries
+__device__ __forceinline__ void tile_init(double *tile, const int lane) {
+    if (lane >= NBUF * NPP) return;
+    double *rec = tile + (lane / NPP) * BUF_LEN + slot_offset(lane % NPP);
 #pragma unroll
     for (int j = 0; j < REC; j += 2) st2(rec + j, 0.0, 0.0);
     rec[1] = -1.0;   // F1 d/dx
@@ -251,7 +279,7 @@ __device__ __forceinline__ void wind_cube(const FgConst &c, const double xn, con
 //
 // sx: the warp's staged x slice (slot 0 = x[11*k0], node j of the slice at sx[1+11j]).  Once every lane
 // has its window in registers the slice is dead and serves as staging area for F and the objective row.
-// tile: the warp's NBUF x NPP record slots, constants already in place (record_init).
+// tile: the warp's NBUF x NPP record slots, constants already in place (tile_init).
 // needG carries two experiment switches in bits 2 and 3 (tools/kbench.py): 4 = stage but do not store
 // G, 8 = no trigonometry.
 template <int FORM, int WIND, int MODE>
@@ -441,6 +469,10 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
 
     // ---- Jacobian rows, src/problem.cpp:1074-1192 ----
     double v[NVAR];
+    if (needG & 16) {  // experiment switch: no Jacobian arithmetic, the drain alone
+#pragma unroll
+        for (int i = 0; i < NVAR; i++) v[i] = Va + (double)i;
+    } else {
     v[0] = -vx;  // F1 :1084-1088
     v[1] = mdt * cc * cg;
     v[2] = Vadt * cc * sg;
@@ -498,6 +530,7 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
     }
     v[29] = -dphi;  // F7 :1172
     v[30] = -dCL;   // F8 :1184
+    }
 
     if (MODE == MODE_COMPACT) {
         // compact G: the warp's windows as NVAR doubles each, contiguous at Gb + R0 + NVAR*k; staged in the
@@ -531,33 +564,36 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
         return;
     }
 
-    // ---- drain: groups of NPP windows through the two record buffers, whole records to global ----
-    // Group g (windows k0+NPP*g ..) fills buffer g&1 while the TMA unit may still be reading the other
-    // one; lane 0 issues every bulk copy (NPP contiguous records = NPP*832 bytes) and owns the bulk
-    // groups.  The buffers are dense, as the copy needs: the NPP lanes of a group store at a stride of
-    // 832 bytes, a 2-way bank conflict.
+    // ---- drain: passes of NPP windows through the record buffer(s), whole records to global ----
+    // Pass g (windows k0+NPP*g ..) fills buffer g % NBUF once the TMA unit has read what the buffer held
+    // before; lane 0 issues the pass's bulk copies (one per dense run of UNIT records) as one bulk group.
     double *Grec = Gb + c.R0 + (size_t)REC * k0;  // record of window k0
     const bool bulk = (reinterpret_cast<uintptr_t>(Grec) & 15) == 0;
 #pragma unroll 1
     for (int g = 0; g < 32 / NPP; g++) {
         if (g * NPP >= nk) break;
-        double *buf = tile + (g & 1) * (NPP * REC);
+        double *buf = tile + (g % NBUF) * BUF_LEN;
         if (bulk && g >= NBUF) {
-            if (lane == 0) bulk_wait_read<NBUF - 1>();  // group g-2 has been read: its buffer is free
+            if (lane == 0) bulk_wait_read<NBUF - 1>();  // pass g-NBUF has been read: its buffer is free
             __syncwarp();
         }
-        if ((lane / NPP) == g) record_store(buf + (lane & (NPP - 1)) * REC, v, mdt);
-        const int cnt = min(NPP, nk - g * NPP) * REC;
+        if ((lane / NPP) == g) record_store(buf + slot_offset(lane & (NPP - 1)), v, mdt);
+        const int nrec = min(NPP, nk - g * NPP);
         double *dst = Grec + (size_t)REC * NPP * g;
         if (needG & 4) {
             __syncwarp();
         } else if (bulk) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) bulk_store(dst, buf, cnt * 8);
+            if (lane == 0) {
+#pragma unroll
+                for (int u = 0; u < NPP / UNIT; u++)
+                    if (u * UNIT < nrec) bulk_issue(dst + u * UNIT * REC, buf + u * USTR, min(UNIT, nrec - u * UNIT) * REC * 8);
+                bulk_commit();
+            }
         } else {
             __syncwarp();
-            for (int i = lane; i < cnt; i += 32) dst[i] = buf[i];
+            for (int i = lane; i < nrec * REC; i += 32) dst[i] = buf[(i / (UNIT * REC)) * USTR + i % (UNIT * REC)];
             __syncwarp();
         }
     }
@@ -682,9 +718,8 @@ __device__ __forceinline__ void traj_epilogue(const FgConst &c, const int lane, 
 // grid.x = B, blockDim.x = 32*ceil(ts/32) (<= MAXT).  Warp w owns windows 32w..32w+31 and runs on its
 // own after start-up; the cost sum crosses warps through shared memory and an arrival counter, and the
 // last warp to arrive runs the trajectory epilogue.
-template <int FORM, int WIND, int MAXT, int MINB, int MODE>
-__global__ void __launch_bounds__(MAXT, MINB)
-fg_cta_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, long ldx,
+template <int FORM, int WIND, int MODE>
+__device__ __forceinline__ void fg_cta_body(const FgConst &c, const double *__restrict__ x, long ldx,
               double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG,
               double *__restrict__ S, long ldS) {
     constexpr bool SUMM = (MODE == MODE_SUMMARY);
@@ -711,7 +746,7 @@ fg_cta_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, l
         n0 = __ldg(xb + 1 + lane);
         ne = __ldg(xb + (size_t)PX * ts + 1 + lane);
     }
-    if (needG && lane < NBUF * NPP) record_init(tile + lane * REC);
+    if (needG) tile_init(tile, lane);
     if (threadIdx.x == 0) arrivals = 0;
     __syncthreads();
     cp_async_wait<0>();
@@ -752,6 +787,23 @@ fg_cta_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, l
                         MODE == MODE_COMPACT ? NVAR : REC);
 }
 
+template <int FORM, int WIND, int MAXT, int MINB, int MODE>
+__global__ void __launch_bounds__(MAXT, MINB)
+fg_cta_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, long ldx,
+              double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG,
+              double *__restrict__ S, long ldS) {
+    fg_cta_body<FORM, WIND, MODE>(c, x, ldx, F, ldF, G, ldG, needF, needG, S, ldS);
+}
+
+// same body under an explicit register cap (experiment: 7-warp CTAs at 96 registers = 3 CTAs / SM)
+template <int FORM, int WIND, int MAXT, int NREG, int MODE>
+__global__ void __launch_bounds__(MAXT) __maxnreg__(NREG)
+fg_cta_kernel_r(const __grid_constant__ FgConst c, const double *__restrict__ x, long ldx,
+                double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG,
+                double *__restrict__ S, long ldS) {
+    fg_cta_body<FORM, WIND, MODE>(c, x, ldx, F, ldF, G, ldG, needF, needG, S, ldS);
+}
+
 // ---- kernel B: persistent warps, one trajectory per warp at a time ------------------------------------------
 //
 // Every warp walks trajectories b = warp_id, warp_id + total_warps, ... and, within a trajectory, its
@@ -776,7 +828,7 @@ fg_warp_kernel(const __grid_constant__ FgConst c, int B, const double *__restric
 
     slice_prefetch(wsm, x + (size_t)b * ldx, 1 + PX * (min(32, ts) + 1), lane);
     cp_async_commit();
-    if (needG && lane < NBUF * NPP) record_init(tile + lane * REC);
+    if (needG) tile_init(tile, lane);
     double dt = 0.0, n0 = 0.0, accT = 0.0, accp = 0.0, accm = 0.0, accq = 0.0;
 #pragma unroll 1
     while (b < B) {
@@ -839,6 +891,21 @@ cudaError_t launch_cta(const FgLaunch &L) {
     return cudaGetLastError();
 }
 
+template <int FORM, int WIND, int MAXT, int NREG, int MODE>
+cudaError_t launch_cta_r(const FgLaunch &L) {
+    auto kern = fg_cta_kernel_r<FORM, WIND, MAXT, NREG, MODE>;
+    const int nthr = 32 * ((L.c->ts + 31) / 32);
+    const size_t smem = sizeof(double) * (size_t)(nthr / 32) * WARP_SMEM;
+    static size_t configured = 0;  // per instantiation
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    kern<<<L.B, nthr, smem, L.stream>>>(*L.c, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG, L.S, L.ldS);
+    return cudaGetLastError();
+}
+
 template <int FORM, int WIND, int WARPS, int MINB, int MODE>
 cudaError_t launch_warp(const FgLaunch &L) {
     auto kern = fg_warp_kernel<FORM, WIND, WARPS, MINB, MODE>;
@@ -865,6 +932,9 @@ cudaError_t launch_sel(const FgLaunch &L) {
     const int ts = L.c->ts;
     if (L.kernel == 2 || ts > 256) return launch_warp<FORM, WIND, 4, 4, MODE>(L);  // 128 registers, 16 warps / SM
     if (ts <= 128) return launch_cta<FORM, WIND, 128, 4, MODE>(L);                 // 128 registers, 16 warps / SM
+    if (L.kernel == 3 && ts <= 224) return launch_cta_r<FORM, WIND, 224, 96, MODE>(L);   // experiment: 96 registers, 21 warps / SM
+    if (L.kernel == 4 && ts <= 224) return launch_cta_r<FORM, WIND, 224, 104, MODE>(L);  // experiment
+    if (L.kernel == 5 && ts <= 224) return launch_cta_r<FORM, WIND, 224, 112, MODE>(L);  // experiment
     return launch_cta<FORM, WIND, 256, 2, MODE>(L);                          // 128 registers, 14-16 warps / SM
 }
 

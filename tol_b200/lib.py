@@ -4,7 +4,7 @@ fallback."""
 import ctypes as C
 import os
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtolcuda.so")
+LIB_PATH = os.environ.get("TOLCUDA_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtolcuda.so")
 
 
 class TolcudaError(RuntimeError):

@@ -44,7 +44,8 @@ st = torch.cuda.Stream()
 ev.set_stream(st.cuda_stream)
 needF, needG = "F" in args.need, "G" in args.need
 if needG:  # experiment switches ride on the needG flag bits of the launch (G4 = no stores, G8 = no trig)
-    needG = 1 + sum(int(ch) for ch in args.need if ch.isdigit())
+    digits = "".join(ch for ch in args.need if ch.isdigit())  # FG4 = no G stores, FG8 = no trig, FG16 = no Jacobian arithmetic, sums allowed (FG24)
+    needG = 1 + (int(digits) if digits else 0)
 with torch.cuda.stream(st):
     for _ in range(args.warmup):
         ev.eval_batch_device(Xd, Fd, Gd, needF, needG, sync=False)
