@@ -577,14 +577,17 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
             if (lane == 0) bulk_wait_read<NBUF - 1>();  // pass g-NBUF has been read: its buffer is free
             __syncwarp();
         }
-        if ((lane / NPP) == g) record_store(buf + slot_offset(lane & (NPP - 1)), v, mdt);
+        if ((lane / NPP) == g) {
+            record_store(buf + slot_offset(lane & (NPP - 1)), v, mdt);
+            // the writers make their generic-proxy stores visible to the async proxy (the TMA unit) ...
+            if (bulk && !(needG & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
         const int nrec = min(NPP, nk - g * NPP);
         double *dst = Grec + (size_t)REC * NPP * g;
         if (needG & 4) {
             __syncwarp();
         } else if (bulk) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
+            __syncwarp();  // ... and lane 0 issues the copies after all of them have done so
             if (lane == 0) {
 #pragma unroll
                 for (int u = 0; u < NPP / UNIT; u++)
