@@ -123,6 +123,18 @@ int tolcuda_problem_pattern(int formulation, int ts, int *iGfun, int *jGvar);
 int tolcuda_problem_initial_guess(const tolcuda_config *cfg, double *x0);
 int tolcuda_problem_bounds(const tolcuda_config *cfg, double *xlow, double *xupp, double *Flow,
                            double *Fupp);
+/* Result files of a finished solve (host only, no CUDA), byte for byte what the reference writes:
+ *   JSON  problem::writeJSON src/problem.cpp:1247-1365 -- "snopt_results.json" (src/tol.cpp:30), the file the
+ *         mission layer reads back (msl/mission.py:204-240): args, problem, FinalCost, dt, trajectory
+ *         {time,x,y,z,Va,gam,chi,phi,CL,dphi,dCL,T}, aircraft, gains, limits, snopt; jsoncpp StyledWriter layout
+ *   TXT   problem::writeTXT src/problem.cpp:1371-1418 (the reference ignores its file-name argument and always
+ *         writes "snopt_output.txt"; here `path` is honoured)
+ * aircraft/mission: the names given on the reference command line; east,north,up: its first three arguments;
+ * x[n]: decision vector; final_cost: F[0].  cfg->limits and cfg->solver_tol must be filled (they are after
+ * tolcuda_create_from_files + tolcuda_get_config). */
+int tolcuda_write_results_json(const tolcuda_config *cfg, const char *aircraft, const char *mission, double east,
+                               double north, double up, const double *x, double final_cost, const char *path);
+int tolcuda_write_results_txt(const tolcuda_config *cfg, const double *x, double final_cost, const char *path);
 /* the configuration a handle was created with (e.g. after tolcuda_create_from_files) */
 int tolcuda_get_config(tolcuda_handle h, tolcuda_config *cfg);
 

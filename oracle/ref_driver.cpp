@@ -337,4 +337,21 @@ void tolref_usrfun_many(void *hv, int count, const double *x, long ldx, double *
         tolref_usrfun(hv, x + b * ldx, 1, F + b * ldF, 1, G + b * ldG);
 }
 
+/* the reference's result writers (src/problem.cpp:1247-1365, 1371-1418) on a given state: x and F[0] are
+ * copied into the arrays the writers read.  writeJSON honours its file name; writeTXT ignores it and always
+ * writes "snopt_output.txt" into the current directory (through fopen: switch null-IO off first). */
+void tolref_write_json(void *hv, const double *x, double F0, const char *path) {
+    Handle *h = (Handle *)hv;
+    memcpy(FIELD(h, x), x, sizeof(double) * FIELD(h, n));
+    FIELD(h, F)[0] = F0;
+    h->base()->writeJSON(path);
+}
+
+void tolref_write_txt(void *hv, const double *x, double F0) {
+    Handle *h = (Handle *)hv;
+    memcpy(FIELD(h, x), x, sizeof(double) * FIELD(h, n));
+    FIELD(h, F)[0] = F0;
+    h->base()->writeTXT("snopt_results.txt");
+}
+
 } /* extern "C" */

@@ -42,6 +42,8 @@ def lib():
         for f in (L.tolref_eval_many, L.tolref_usrfun_many):
             f.argtypes = [C.c_void_p, C.c_int, dp, C.c_long, dp, C.c_long, dp, C.c_long]
         L.tolref_set_null_io.argtypes = [C.c_int]
+        L.tolref_write_json.argtypes = [C.c_void_p, dp, C.c_double, C.c_char_p]
+        L.tolref_write_txt.argtypes = [C.c_void_p, dp, C.c_double]
         _lib = L
     return _lib
 
@@ -153,6 +155,26 @@ class RefProblem:
         if self.mission != "S10":
             return np.zeros(0, np.int64)
         return self.neG - 3 * self.nb + 3 * np.arange(self.nb)
+
+    def write_json(self, x, F0, path):
+        """reference problem::writeJSON (src/problem.cpp:1247-1365) for the state (x, F[0])"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        lib().tolref_write_json(self.h, _dp(x), C.c_double(F0), str(path).encode())
+
+    def write_txt(self, x, F0, directory):
+        """reference problem::writeTXT (src/problem.cpp:1371-1418): always writes snopt_output.txt into
+        the current directory, so run it from `directory`; returns the file's path"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        L = lib()
+        cwd = os.getcwd()
+        os.chdir(directory)
+        try:
+            L.tolref_set_null_io(0)
+            L.tolref_write_txt(self.h, _dp(x), C.c_double(F0))
+        finally:
+            L.tolref_set_null_io(1)
+            os.chdir(cwd)
+        return os.path.join(directory, "snopt_output.txt")
 
     def eval(self, x, full_callback=False):
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -265,10 +265,18 @@ def test_tolbatch_driver_end_to_end(tmp_path):
         outs = []
         for run in range(2):
             js = str(tmp_path / ("r%d.json" % run))
-            r = subprocess.run([exe] + args + ["--root", root, "--batch", "300", "--steps", "1", "--json", js],
+            r = subprocess.run([exe] + args + ["--root", root, "--batch", "300", "--steps", "1", "--json", js,
+                                               "--results", str(tmp_path), "--nresults", "2"],
                                capture_output=True, text=True, timeout=120)
             assert r.returncode == 0, r.stdout + r.stderr
             outs.append(json.load(open(js)))
+            # trajectory 0 is the reference's x0: its snopt_results.json is the reference's own file for x0
+            ref_json = os.path.join(ROOT, "tests", "golden", "results", fixture + "_s0.json")
+            if os.path.exists(ref_json):
+                got = json.load(open(tmp_path / "snopt_results_0.json"))
+                want = json.load(open(ref_json))
+                assert abs(got.pop("FinalCost") - want.pop("FinalCost")) <= 1e-12 * abs(g["F"][0, 0])
+                assert got == want
         d = outs[0]
         assert (d["n"], d["neF"], d["neG"], d["nonfinite"]) == (int(g["n"]), int(g["neF"]), int(g["neG"]), 0)
         f0 = d["trajectories"][0]["objective"]

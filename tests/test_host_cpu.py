@@ -184,3 +184,45 @@ def test_compact_expand_many_rows_threads():
     assert T.evaluator.expand_compact_g(m, ts, Gc[:0]).shape == (0, neG)
     with pytest.raises(T.TolcudaError):
         T.evaluator.expand_compact_g(m, ts, Gc[:, :Lc - 1].copy())
+
+
+RESULTS = sorted(os.path.splitext(f)[0] for f in os.listdir(os.path.join(GOLDEN_DIR, "results")) if f.endswith(".json"))
+
+
+def _config_from_golden(g):
+    lm = g["lm"]  # member order dtmin,dtmax,xmax,ymax,zmax,xmin,ymin,zmin -> file order
+    sn = g["sn"]
+    return T.make_config(str(g["mission"]), int(g["ts"]), g["ac"], g["gn"], g["goal_ned"],
+                         limits=[lm[0], lm[1], lm[5], lm[2], lm[6], lm[3], lm[7], lm[4]], solver_tol=[sn[4], sn[5]])
+
+
+@pytest.mark.parametrize("case", RESULTS)
+def test_result_files_equal_the_references_byte_for_byte(case, tmp_path):
+    """tolcuda_write_results_json / _txt against the files the UNMODIFIED reference wrote for the same state
+    (oracle/gen_results_golden.py): jsoncpp StyledWriter layout incl. one-line short arrays, %.17g reals,
+    -0, integer-valued reals, the text table's %-4.7e columns"""
+    name, s = case.rsplit("_s", 1)
+    g = load_golden(name)
+    cfg = _config_from_golden(g)
+    x, F0 = g["x"][int(s)], g["F"][int(s), 0]
+    js, tx = tmp_path / "snopt_results.json", tmp_path / "snopt_output.txt"
+    T.write_results_json(cfg, str(g["aircraft"]), str(g["mission"]), g["enu"], x, F0, js)
+    T.write_results_txt(cfg, x, F0, tx)
+    ref = os.path.join(GOLDEN_DIR, "results", case)
+    assert js.read_bytes() == open(ref + ".json", "rb").read()
+    assert tx.read_bytes() == open(ref + ".txt", "rb").read()
+    doc = json.load(open(js))  # and it is the document msl/mission.py:204-240 reads back
+    assert len(doc["trajectory"]["time"]) == int(g["ts"]) + 1 and doc["FinalCost"] == F0
+    with pytest.raises(T.TolcudaError):
+        T.write_results_json(cfg, "a", "S10", (0, 0, 0), x, F0, tmp_path / "no_such_dir" / "r.json")
+
+
+def test_result_json_non_finite_values(tmp_path):
+    """jsoncpp spells NaN as null and infinities as +-1e+9999 (src/jsoncpp.cpp:4054-4066)"""
+    g = load_golden("S10_tempest_ts1")
+    cfg = _config_from_golden(g)
+    x = g["x"][0].copy()
+    x[1], x[2] = np.inf, -np.inf
+    T.write_results_json(cfg, "tempest", "S10", (0, 0, 70), x, float("nan"), tmp_path / "r.json")
+    txt = (tmp_path / "r.json").read_text()
+    assert '"FinalCost" : null' in txt and "[ 1e+9999," in txt and "[ -1e+9999," in txt

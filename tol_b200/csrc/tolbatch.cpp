@@ -8,6 +8,8 @@
 //
 //   tolbatch E N U Eg Ng Ug Rg aircraft mission [--root DIR/] [--ts N] [--batch B] [--gpus G]
 //            [--seed S] [--perturb REL,ABS] [--x-file raw_f64] [--steps K] [--json out.json]
+//            [--results DIR [--nresults K]]   the reference's snopt_results.json (src/problem.cpp:1247-1365)
+//                                             for the first K trajectories, as DIR/snopt_results_<b>.json
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -24,8 +26,8 @@ namespace {
 
 struct Args {
     double enu[3] = {0, 0, 0}, goal[4] = {0, 0, 0, 0};
-    std::string aircraft, mission, root = "./", xfile, json;
-    int ts = 0, batch = 4096, gpus = 0, steps = 3;
+    std::string aircraft, mission, root = "./", xfile, json, results;
+    int ts = 0, batch = 4096, gpus = 0, steps = 3, nresults = 4;
     uint64_t seed = 1;
     double rel = 0.05, abs_ = 0.01;
 };
@@ -75,6 +77,8 @@ Args parse(int argc, char **argv) {
         else if (k == "--seed") a.seed = std::strtoull(val(), nullptr, 10);
         else if (k == "--x-file") a.xfile = val();
         else if (k == "--json") a.json = val();
+        else if (k == "--results") a.results = val();
+        else if (k == "--nresults") a.nresults = std::atoi(val());
         else if (k == "--perturb") {
             if (std::sscanf(val(), "%lf,%lf", &a.rel, &a.abs_) != 2) die("--perturb wants REL,ABS");
         } else die("unknown option " + k);
@@ -187,6 +191,13 @@ int main(int argc, char **argv) {
         std::fprintf(f, " ]\n}\n");
         std::fclose(f);
     }
+    if (!a.results.empty())
+        for (int b = 0; b < std::min(B, a.nresults); b++) {
+            const std::string path = a.results + "/snopt_results_" + std::to_string(b) + ".json";
+            check(tolcuda_write_results_json(&cfg, a.aircraft.c_str(), a.mission.c_str(), a.enu[0], a.enu[1], a.enu[2],
+                                             X + (size_t)b * ldx, obj[b], path.c_str()),
+                  "tolcuda_write_results_json");
+        }
     for (int g = 0; g < G; g++) tolcuda_destroy(h[g]);
     tolcuda_host_free(X), tolcuda_host_free(F), tolcuda_host_free(Gv);
     return nonfinite ? 1 : 0;

@@ -395,6 +395,17 @@ int tolcuda_problem_bounds(const tolcuda_config *cfg, double *xlow, double *xupp
     return 0;
 }
 
+int tolcuda_write_results_json(const tolcuda_config *cfg, const char *aircraft, const char *mission, double east,
+                               double north, double up, const double *x, double final_cost, const char *path) {
+    if (!config_ok(cfg) || !aircraft || !mission || !x || !path) return TOLCUDA_EINVAL;
+    return write_results_json(*cfg, aircraft, mission, east, north, up, x, final_cost, path);
+}
+
+int tolcuda_write_results_txt(const tolcuda_config *cfg, const double *x, double final_cost, const char *path) {
+    if (!config_ok(cfg) || !x || !path) return TOLCUDA_EINVAL;
+    return write_results_txt(*cfg, x, final_cost, path);
+}
+
 int tolcuda_get_config(tolcuda_handle h, tolcuda_config *cfg) {
     if (!h || !cfg) return TOLCUDA_EINVAL;
     *cfg = h->cfg;

@@ -50,6 +50,11 @@ private:
 
 void expand_rows(HostPool &pool, int form, int ts, long B, const double *Gc, long ldGc, double *G, long ldG);
 
+// results.cpp: the reference's two result files
+int write_results_json(const tolcuda_config &cfg, const char *aircraft, const char *mission, double east,
+                       double north, double up, const double *x, double final_cost, const char *path);
+int write_results_txt(const tolcuda_config &cfg, const double *x, double final_cost, const char *path);
+
 int read_params(const std::string &path, std::vector<double> &out);
 int read_aircraft(const std::string &root, const std::string &name, double ac[15]);
 int read_gains(const std::string &root, const std::string &mission, double gn[5]);

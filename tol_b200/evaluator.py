@@ -69,6 +69,20 @@ def bounds(cfg):
     return xl, xu, fl, fu
 
 
+def write_results_json(cfg, aircraft, mission, enu, x, final_cost, path):
+    """reference problem::writeJSON (snopt_results.json), byte for byte"""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    _l.check(_l.load().tolcuda_write_results_json(C.byref(cfg), aircraft.encode(), mission.encode(),
+                                                  *[float(v) for v in enu], _dp(x), float(final_cost),
+                                                  str(path).encode()))
+
+
+def write_results_txt(cfg, x, final_cost, path):
+    """reference problem::writeTXT (snopt_output.txt), byte for byte"""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    _l.check(_l.load().tolcuda_write_results_txt(C.byref(cfg), _dp(x), float(final_cost), str(path).encode()))
+
+
 def padded_ld(n):
     return int(_l.load().tolcuda_padded_ld(int(n)))
 

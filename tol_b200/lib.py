@@ -43,6 +43,9 @@ def load():
     L.tolcuda_problem_pattern.argtypes = [C.c_int, C.c_int, ip, ip]
     L.tolcuda_problem_initial_guess.argtypes = [C.POINTER(Config), dp]
     L.tolcuda_problem_bounds.argtypes = [C.POINTER(Config), dp, dp, dp, dp]
+    L.tolcuda_write_results_json.argtypes = [C.POINTER(Config), C.c_char_p, C.c_char_p, C.c_double, C.c_double,
+                                             C.c_double, dp, C.c_double, C.c_char_p]
+    L.tolcuda_write_results_txt.argtypes = [C.POINTER(Config), dp, C.c_double, C.c_char_p]
     L.tolcuda_get_config.argtypes = [vp, C.POINTER(Config)]
     L.tolcuda_eval.argtypes = [vp, dp, C.c_int, dp, C.c_int, dp]
     L.tolcuda_eval_batch.argtypes = [vp, C.c_int, vp, C.c_long, vp, C.c_long, vp, C.c_long, C.c_int]
