@@ -13,7 +13,9 @@ the whole batch = one kernel launch.
   value     device-resident: x, F, G live in HBM; K launches timed with CUDA events on the launching
             stream; 13.2 GB touched per step >> 126 MB L2, so no L2 flush is needed.
   e2e       the same pass through tolcuda_eval_batch with HOST (pinned) x, F, G: chunked
-            H2D -> kernel -> D2H inside the timed region.
+            H2D -> kernel -> D2H inside the timed region; full F and G rows are in host memory at the end
+            of every step.  Default path: G crosses PCIe as compact rows and the library's host threads
+            write the caller's rows; e2e.full_g_copy is the same call with every G value crossing PCIe.
   roofline  algorithmic bytes 8*(n+neF+neG) per trajectory / average launch duration / measured HBM peak.
   cpu_baseline (N=1)  the reference's own CPU path (oracle/_ref, unmodified sources, -O2) on all host
             cores as independent processes, on a bounded sample of the same batch.

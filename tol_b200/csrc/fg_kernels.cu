@@ -798,15 +798,6 @@ fg_cta_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, l
     fg_cta_body<FORM, WIND, MODE>(c, x, ldx, F, ldF, G, ldG, needF, needG, S, ldS);
 }
 
-// same body under an explicit register cap (experiment: 7-warp CTAs at 96 registers = 3 CTAs / SM)
-template <int FORM, int WIND, int MAXT, int NREG, int MODE>
-__global__ void __launch_bounds__(MAXT) __maxnreg__(NREG)
-fg_cta_kernel_r(const __grid_constant__ FgConst c, const double *__restrict__ x, long ldx,
-                double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG,
-                double *__restrict__ S, long ldS) {
-    fg_cta_body<FORM, WIND, MODE>(c, x, ldx, F, ldF, G, ldG, needF, needG, S, ldS);
-}
-
 // ---- kernel B: persistent warps, one trajectory per warp at a time ------------------------------------------
 //
 // Every warp walks trajectories b = warp_id, warp_id + total_warps, ... and, within a trajectory, its
@@ -894,21 +885,6 @@ cudaError_t launch_cta(const FgLaunch &L) {
     return cudaGetLastError();
 }
 
-template <int FORM, int WIND, int MAXT, int NREG, int MODE>
-cudaError_t launch_cta_r(const FgLaunch &L) {
-    auto kern = fg_cta_kernel_r<FORM, WIND, MAXT, NREG, MODE>;
-    const int nthr = 32 * ((L.c->ts + 31) / 32);
-    const size_t smem = sizeof(double) * (size_t)(nthr / 32) * WARP_SMEM;
-    static size_t configured = 0;  // per instantiation
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
-    kern<<<L.B, nthr, smem, L.stream>>>(*L.c, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG, L.S, L.ldS);
-    return cudaGetLastError();
-}
-
 template <int FORM, int WIND, int WARPS, int MINB, int MODE>
 cudaError_t launch_warp(const FgLaunch &L) {
     auto kern = fg_warp_kernel<FORM, WIND, WARPS, MINB, MODE>;
@@ -935,9 +911,6 @@ cudaError_t launch_sel(const FgLaunch &L) {
     const int ts = L.c->ts;
     if (L.kernel == 2 || ts > 256) return launch_warp<FORM, WIND, 4, 4, MODE>(L);  // 128 registers, 16 warps / SM
     if (ts <= 128) return launch_cta<FORM, WIND, 128, 4, MODE>(L);                 // 128 registers, 16 warps / SM
-    if (L.kernel == 3 && ts <= 224) return launch_cta_r<FORM, WIND, 224, 96, MODE>(L);   // experiment: 96 registers, 21 warps / SM
-    if (L.kernel == 4 && ts <= 224) return launch_cta_r<FORM, WIND, 224, 104, MODE>(L);  // experiment
-    if (L.kernel == 5 && ts <= 224) return launch_cta_r<FORM, WIND, 224, 112, MODE>(L);  // experiment
     return launch_cta<FORM, WIND, 256, 2, MODE>(L);                          // 128 registers, 14-16 warps / SM
 }
 
