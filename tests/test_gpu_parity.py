@@ -362,3 +362,69 @@ def test_fused_trajectory_summary(name, kernel, monkeypatch):
     Fr, Gr = ev.eval_batch_host(X)
     assert np.array_equal(F, Fr) and np.array_equal(G, Gr)
     ev.close()
+
+
+def _read_snmock_log(path):
+    b = open(path, "rb").read()
+    N, NF, NG, objrow = np.frombuffer(b[:16], np.int32)
+    off = 16
+    iG = np.frombuffer(b[off:off + 4 * NG], np.int32)
+    jG = np.frombuffer(b[off + 4 * NG:off + 8 * NG], np.int32)
+    off += 8 * NG
+    calls = []
+    while off < len(b):
+        st, nf, ng = np.frombuffer(b[off:off + 12], np.int32)
+        v = np.frombuffer(b[off + 12:off + 12 + 8 * (N + NF + NG)])
+        calls.append((int(st), int(nf), int(ng), v[:N], v[N:N + NF], v[N + NF:]))
+        off += 12 + 8 * (N + NF + NG)
+    return int(objrow), iG, jG, calls
+
+
+@pytest.mark.parametrize("args,fixture", [
+    (["0", "0", "70", "0", "-100", "0", "100", "tempest", "S10"], "S10_tempest_ts100"),
+    (["0", "0", "70", "400", "0", "0", "0", "skywalker", "G7"], "G7_skywalker_ts100")])
+def test_reference_driver_with_libtolcuda_dropped_in(args, fixture, tmp_path):
+    """The drop-in itself, executed: the UNMODIFIED reference driver objects (problem::runSNOPT ->
+    snoptProblemA::solve -> f_snkera -> usrfun, then writeJSON) linked once with the reference's DefineFG.o
+    and once with libtolcuda's DEFINEGusrfg_ in its place (oracle/dropin_main.cpp), SNOPT being the stand-in
+    oracle/snmock.cpp that drives the callback with SNOPT's argument conventions (1-based index arrays,
+    Status 1 / 0 / 2, F-only and G-only calls) and steps along the objective gradient it reads from G.
+    Both runs must see the same pattern and agree call by call."""
+    import json
+    import os
+    import subprocess
+    from conftest import ROOT
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "tol_dropin_ref")
+    cuda_exe = os.path.join(ROOT, "oracle", "_ref", "tol_dropin_cuda")
+    root = os.path.join(ROOT, "oracle", "_ref", "params") + "/"
+    if not (os.path.exists(ref_exe) and os.path.exists(cuda_exe) and os.path.isdir(root)):
+        pytest.skip("oracle/_ref drop-in binaries are not built (make -C oracle ref, build container only)")
+    g = load_golden(fixture)
+    logs, docs = {}, {}
+    for tag, exe in (("ref", ref_exe), ("cuda", cuda_exe)):
+        wd = tmp_path / tag
+        wd.mkdir()
+        log = str(wd / "calls.bin")
+        r = subprocess.run([exe] + args + [root], cwd=wd, env=dict(os.environ, SNMOCK_LOG=log, SNMOCK_STEPS="7"),
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        logs[tag] = _read_snmock_log(log)
+        docs[tag] = json.load(open(wd / "snopt_results.json"))
+    (oref, iGr, jGr, cref), (ocuda, iGc, jGc, ccuda) = logs["ref"], logs["cuda"]
+    assert oref == ocuda == 1
+    assert np.array_equal(iGr, g["iGfun"] + 1) and np.array_equal(jGr, g["jGvar"] + 1)  # what SNOPT is handed
+    assert np.array_equal(iGc, iGr) and np.array_equal(jGc, jGr)
+    assert len(cref) == len(ccuda) == 8
+    mask = np.ones(int(g["neG"]), bool)
+    mask[g["ub_mask"]] = False  # left uninitialised by the reference
+    for k, (a, b) in enumerate(zip(cref, ccuda)):
+        assert a[:3] == b[:3] and a[0] == (1 if k == 0 else (2 if k == 7 else 0))
+        assert_parity(b[3], a[3], "call %d x" % k)  # the iterates: same steps taken from the same G
+        assert_parity(b[4], a[4], "call %d F" % k)
+        if k == 0 or a[2]:  # G was requested in this call (otherwise the buffer keeps the last requested one)
+            assert_parity(b[5][mask], a[5][mask], "call %d G" % k)
+    assert_parity(cref[0][4], g["F"][0], "first call = the fixture's x0")
+    # the reference's own writeJSON ran after both "solves": same document up to the parity tolerance
+    assert docs["cuda"]["args"] == docs["ref"]["args"] and docs["cuda"]["snopt"] == docs["ref"]["snopt"]
+    assert abs(docs["cuda"]["FinalCost"] - docs["ref"]["FinalCost"]) <= 1e-14 + 1e-12 * abs(docs["ref"]["FinalCost"])
+    assert_parity(np.array(docs["cuda"]["trajectory"]["x"]), np.array(docs["ref"]["trajectory"]["x"]), "x*")

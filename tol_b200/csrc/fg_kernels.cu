@@ -40,11 +40,14 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "fg_const.h"
 #include "fg_launch.h"
 
 namespace {
 
+constexpr int MAX_DEVICES = 64;  // power of two; device ordinals are folded into it
 constexpr int PX = TOLCUDA_PX;
 constexpr int PF = TOLCUDA_PF;
 constexpr int REC = TOLCUDA_REC;
@@ -875,11 +878,13 @@ cudaError_t launch_cta(const FgLaunch &L) {
     auto kern = fg_cta_kernel<FORM, WIND, MAXT, MINB, MODE>;
     const int nthr = 32 * ((L.c->ts + 31) / 32);
     const size_t smem = sizeof(double) * (size_t)(nthr / 32) * WARP_SMEM;
-    static size_t configured = 0;  // per instantiation
-    if (smem > configured) {
+    // the attribute is per device (and this static per instantiation): tolbatch drives one device per thread
+    static std::atomic<size_t> configured[MAX_DEVICES];
+    std::atomic<size_t> &done = configured[L.device & (MAX_DEVICES - 1)];
+    if (smem > done.load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        done.store(smem, std::memory_order_release);
     }
     kern<<<L.B, nthr, smem, L.stream>>>(*L.c, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG, L.S, L.ldS);
     return cudaGetLastError();
@@ -889,11 +894,12 @@ template <int FORM, int WIND, int WARPS, int MINB, int MODE>
 cudaError_t launch_warp(const FgLaunch &L) {
     auto kern = fg_warp_kernel<FORM, WIND, WARPS, MINB, MODE>;
     const size_t smem = sizeof(double) * (size_t)WARPS * WARP_SMEM_B;
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<size_t> configured[MAX_DEVICES];  // per device, see launch_cta
+    std::atomic<size_t> &done = configured[L.device & (MAX_DEVICES - 1)];
+    if (smem > done.load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        done.store(smem, std::memory_order_release);
     }
     const int resident = L.sm_count * MINB;  // persistent: one wave of CTAs
     const int want = (L.B + WARPS - 1) / WARPS;

@@ -24,6 +24,7 @@ struct FgLaunch {
     int compact;  // G/ldG address the compact layout [R0 | 31 per window | boundary block] (host-pointer path)
     int kernel;    // 0/1 = kernel A (CTA per trajectory), 2 = kernel B (persistent warps)
     int sm_count;  // SMs of the device
+    int device;    // CUDA device ordinal the launch goes to (the current device)
     cudaStream_t stream;
 };
 

@@ -88,6 +88,7 @@ int launch(tolcuda_ctx *h, cudaStream_t st, int B, const double *x, long ldx, do
     L.needF = needF, L.needG = needG;
     L.kernel = h->kernel;
     L.sm_count = h->sm_count;
+    L.device = h->cfg.device;
     L.stream = st;
     cudaError_t e = fg_launch(L);
     if (e != cudaSuccess) return cuda_fail(e, "fg_launch");
