@@ -371,8 +371,8 @@ def run_ours(args, wl_name):
                                 "api": "same call with TOLCUDA_FULL_G_COPY: every G value crosses PCIe"}},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": scaled_traffic(wl_name, alg_bytes), "traffic_source": "profiles/roofline_traffic.json (ncu --set full at B=8192, ratio to algorithmic bytes applied)", "peak_source": peak_src,
-                     "kernel": "fg_cta_kernel<S10, wind 1, 256, 2>", "algorithmic_bytes_per_launch": alg_bytes,
+                     "traffic": scaled_traffic(wl_name, alg_bytes), "traffic_source": "profiles/roofline_traffic.json (ncu --set full capture of the same kernel, ratio to algorithmic bytes applied)", "peak_source": peak_src,
+                     "kernel": "fg_cta_kernel<%s, wind %d, PLAIN>" % (str(g["mission"]), int(g["wind_model"])), "algorithmic_bytes_per_launch": alg_bytes,
                      "launch_ms": launch_ms},
         "clocks": clocks,
     }
