@@ -226,3 +226,25 @@ def test_result_json_non_finite_values(tmp_path):
     T.write_results_json(cfg, "tempest", "S10", (0, 0, 70), x, float("nan"), tmp_path / "r.json")
     txt = (tmp_path / "r.json").read_text()
     assert '"FinalCost" : null' in txt and "[ 1e+9999," in txt and "[ -1e+9999," in txt
+
+
+def test_header_is_plain_c_and_the_callback_has_the_snopta_type(tmp_path):
+    """include/tolcuda.h must compile as C99 (plain pointers and sizes, no C++/CUDA/torch types) and
+    DEFINEGusrfg_ must be assignable to SNOPT's user-function pointer type snFunA as reference
+    include/snopt/snopt.h:60-66 declares it (restated in the test source, not included)."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('''
+#include "tolcuda.h"
+typedef void (*snFunA)(int *Status, int *n, double x[], int *needF, int *neF, double F[], int *needG, int *neG,
+                       double G[], char cu[], int *lencu, int iu[], int *leniu, double ru[], int *lenru);
+snFunA user_function = DEFINEGusrfg_;
+int (*batch)(tolcuda_handle, int, const double *, long, double *, long, double *, long, int) = tolcuda_eval_batch;
+int main(void) { return user_function == 0 || batch == 0 || sizeof(tolcuda_config) != 4 * sizeof(int) + 34 * sizeof(double); }
+''')
+    for cc, std in (("gcc", "-std=c99"), ("g++", "-std=c++11")):
+        exe = tmp_path / ("abi_" + cc)
+        subprocess.check_call([cc, std, "-Wall", "-Wextra", "-Werror", "-pedantic", "-x", "c" if cc == "gcc" else "c++",
+                               "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                               "-L", os.path.dirname(T.LIB_PATH), "-ltolcuda", "-Wl,-rpath," + os.path.dirname(T.LIB_PATH)])
+        assert subprocess.run([str(exe)]).returncode == 0
