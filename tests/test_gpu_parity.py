@@ -428,3 +428,33 @@ def test_reference_driver_with_libtolcuda_dropped_in(args, fixture, tmp_path):
     assert docs["cuda"]["args"] == docs["ref"]["args"] and docs["cuda"]["snopt"] == docs["ref"]["snopt"]
     assert abs(docs["cuda"]["FinalCost"] - docs["ref"]["FinalCost"]) <= 1e-14 + 1e-12 * abs(docs["ref"]["FinalCost"])
     assert_parity(np.array(docs["cuda"]["trajectory"]["x"]), np.array(docs["ref"]["trajectory"]["x"]), "x*")
+
+
+@pytest.mark.parametrize("name", ["S10_tempest_ts100", "G7_skywalker_ts100"])
+def test_degenerate_inputs_are_non_finite_where_the_reference_is(name, oracle_built):
+    """Inputs outside the bounds SNOPT keeps (Va = 0, cos(gamma) = 0, a node exactly on the loiter centre):
+    the reference divides by zero there.  The kernels share reciprocals (x * (1/D) with a correction step), so
+    the KIND of non-finite value can differ (NaN where the reference has +-Inf), but an entry is non-finite
+    exactly where the reference's is, every other entry keeps the parity tolerance, and the other
+    trajectories of the batch are unaffected."""
+    g = load_golden(name)
+    p = port_from_golden(g)
+    ts = int(g["ts"])
+    B = 6
+    X = T.synth.batch(g["x"][0], 31337, 0, B)
+    X[1, 1 + 11 * 5 + 3] = 0.0                    # Va = 0 at node 5
+    X[2, 1 + 11 * 9 + 4] = np.pi / 2              # gamma = 90 deg at node 9
+    X[3, 1 + 11 * 7 + 0], X[3, 1 + 11 * 7 + 1] = g["goal_ned"][0], g["goal_ned"][1]  # node 7 on the goal
+    X[4, 1 + 11 * ts + 0], X[4, 1 + 11 * ts + 1] = X[4, 1], X[4, 2]  # G7: dist = 0
+    Fr, Gr = np.empty((B, p.neF)), np.empty((B, p.neG))
+    with np.errstate(all="ignore"):
+        p.eval_many(X, Fr, Gr)
+    ev = T.Evaluator.from_golden(g)
+    F, G = ev.eval_batch_host(X)
+    ev.close()
+    assert not np.isfinite(Fr[1]).all() or not np.isfinite(Gr[1]).all()  # the cases do hit the singularities
+    for got, ref, what in ((F, Fr, "F"), (G, Gr, "G")):
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(got), fin), what
+        assert_parity(np.where(fin, got, 0.0), np.where(fin, ref, 0.0), name + " degenerate " + what)
+    assert np.isfinite(F[[0, 5]]).all() and np.isfinite(G[[0, 5]]).all()
