@@ -372,7 +372,7 @@ def run_ours(args, wl_name):
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": scaled_traffic(wl_name, alg_bytes), "traffic_source": "profiles/roofline_traffic.json (ncu --set full capture of the same kernel, ratio to algorithmic bytes applied)", "peak_source": peak_src,
-                     "kernel": "fg_cta_kernel<%s, wind %d, PLAIN>" % (str(g["mission"]), int(g["wind_model"])), "algorithmic_bytes_per_launch": alg_bytes,
+                     "kernel": "fg_cta_kernel<%s, wind %d, PLAIN, runs of 2 trajectories per CTA>" % (str(g["mission"]), int(g["wind_model"])), "algorithmic_bytes_per_launch": alg_bytes,
                      "launch_ms": launch_ms},
         "clocks": clocks,
     }

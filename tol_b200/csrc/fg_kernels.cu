@@ -112,11 +112,24 @@ __device__ __forceinline__ void st2(double *p, double a, double b) {
 }
 
 // ---- asynchronous copies ---------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(double *dst, const double *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
+//
+// Shared-memory operands are 32-bit shared-window addresses computed ONCE per kernel (smem_addr): converting
+// a generic pointer at every use costs an S2R of the CTA's cluster rank plus address arithmetic each time,
+// and inside the kernels' loops ptxas re-materialises that instead of keeping it.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// thread index read ONCE: as a plain threadIdx.x expression ptxas re-reads the special register (S2R, tens of
+// cycles on the MIO path) at every use inside the kernels' loops when registers are tight; a volatile asm
+// result cannot be re-materialised
+__device__ __forceinline__ int thread_index() {
+    int t;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+    return t;
 }
-__device__ __forceinline__ void cp_async8(double *dst, const double *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
+__device__ __forceinline__ void cp_async16(uint32_t dst, const double *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const double *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -124,29 +137,27 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// enqueue the copy of `cnt` doubles xs[0..cnt) into sx[0..cnt): 16-byte pieces when xs allows it
-__device__ __forceinline__ void slice_prefetch(double *sx, const double *xs, const int cnt, const int lane) {
+// enqueue the copy of `cnt` doubles xs[0..cnt) to shared address sx_s: 16-byte pieces when xs allows it
+__device__ __forceinline__ void slice_prefetch(const uint32_t sx_s, const double *xs, const int cnt, const int lane) {
     if ((reinterpret_cast<uintptr_t>(xs) & 15) == 0) {
 #pragma unroll
         for (int it = 0; it < (SX_LEN / 2 + 31) / 32; it++) {
             const int i = lane + 32 * it;
-            if (2 * i + 1 < cnt) cp_async16(sx + 2 * i, xs + 2 * i);
-            else if (2 * i < cnt) cp_async8(sx + 2 * i, xs + 2 * i);
+            if (2 * i + 1 < cnt) cp_async16(sx_s + 16 * i, xs + 2 * i);
+            else if (2 * i < cnt) cp_async8(sx_s + 16 * i, xs + 2 * i);
         }
     } else {
-        for (int i = lane; i < cnt; i += 32) cp_async8(sx + i, xs + i);
+        for (int i = lane; i < cnt; i += 32) cp_async8(sx_s + 8 * i, xs + i);
     }
 }
 
-// TMA bulk copy shared -> global of `bytes` (a multiple of 16; both sides 16-byte aligned), as its own
-// bulk group of the calling thread
-__device__ __forceinline__ void bulk_issue(double *gdst, const double *ssrc, const int bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-                 "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+// TMA bulk copy shared -> global of `bytes` (a multiple of 16; both sides 16-byte aligned)
+__device__ __forceinline__ void bulk_issue(double *gdst, const uint32_t ssrc, const int bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes)
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_store(double *gdst, const double *ssrc, const int bytes) {
+__device__ __forceinline__ void bulk_store(double *gdst, const uint32_t ssrc, const int bytes) {
     bulk_issue(gdst, ssrc, bytes);
     bulk_commit();
 }
@@ -286,7 +297,7 @@ __device__ __forceinline__ void wind_cube(const FgConst &c, const double xn, con
 // needG carries two experiment switches in bits 2 and 3 (tools/kbench.py): 4 = stage but do not store
 // G, 8 = no trigonometry.
 template <int FORM, int WIND, int MODE>
-__device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *tile, const double dt,
+__device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *tile, const uint32_t tile_s, const double dt,
                                           const int k0, const int nk, const int lane,
                                           double *__restrict__ Fb, double *__restrict__ Gb,
                                           const int needF, const int needG, TileSums &ts_out) {
@@ -554,7 +565,7 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) {
-                    bulk_store(dst, tile, cnt * 8);
+                    bulk_store(dst, tile_s, cnt * 8);
                     bulk_wait_read<0>();
                 }
                 __syncwarp();
@@ -594,7 +605,8 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
             if (lane == 0) {
 #pragma unroll
                 for (int u = 0; u < NPP / UNIT; u++)
-                    if (u * UNIT < nrec) bulk_issue(dst + u * UNIT * REC, buf + u * USTR, min(UNIT, nrec - u * UNIT) * REC * 8);
+                    if (u * UNIT < nrec)
+                        bulk_issue(dst + u * UNIT * REC, tile_s + 8 * ((g % NBUF) * BUF_LEN + u * USTR), min(UNIT, nrec - u * UNIT) * REC * 8);
                 bulk_commit();
             }
         } else {
@@ -612,11 +624,11 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
 // Out-of-line instance for the persistent kernel: inlined into its trajectory/tile loop, ptxas keeps
 // dozens of extra values live across the loop and spills; as a call the tile body is allocated on its own.
 template <int FORM, int WIND, int MODE>
-__device__ __noinline__ void tile_eval_call(const FgConst &c, double *sx, double *tile, const double dt,
+__device__ __noinline__ void tile_eval_call(const FgConst &c, double *sx, double *tile, const uint32_t tile_s, const double dt,
                                             const int k0, const int nk, const int lane,
                                             double *__restrict__ Fb, double *__restrict__ Gb,
                                             const int needF, const int needG, TileSums &ts_out) {
-    tile_eval<FORM, WIND, MODE>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, ts_out);
+    tile_eval<FORM, WIND, MODE>(c, sx, tile, tile_s, dt, k0, nk, lane, Fb, Gb, needF, needG, ts_out);
 }
 
 // ---- end of a trajectory: F[0], boundary rows, objective-row ends --------------------------------------
@@ -719,86 +731,107 @@ __device__ __forceinline__ void traj_epilogue(const FgConst &c, const int lane, 
     }
 }
 
-// ---- kernel A: one CTA per trajectory ------------------------------------------------------------------
+// ---- kernel A: one CTA per run of `per` consecutive trajectories ------------------------------------------------
 //
-// grid.x = B, blockDim.x = 32*ceil(ts/32) (<= MAXT).  Warp w owns windows 32w..32w+31 and runs on its
-// own after start-up; the cost sum crosses warps through shared memory and an arrival counter, and the
-// last warp to arrive runs the trajectory epilogue.
-template <int FORM, int WIND, int MODE>
-__device__ __forceinline__ void fg_cta_body(const FgConst &c, const double *__restrict__ x, long ldx,
-              double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG,
-              double *__restrict__ S, long ldS) {
+// blockDim.x = 32*ceil(ts/32) (<= MAXT).  Warp w owns windows 32w..32w+31 of every trajectory of the run and
+// works on its own after start-up; the cost sums of a trajectory cross warps through shared memory and an
+// arrival counter, and the last warp to arrive runs that trajectory's epilogue.  The warp's two x-slice buffers
+// form a ring: the slices of the first two trajectories are requested at start-up, the slice of trajectory
+// t+2 as soon as trajectory t has left its buffer, so from the second trajectory on neither the CTA launch nor
+// the x load is on the critical path, and the record slots' constants are written once per run.  Measured
+// (S10 ts=200, B=65,536): per = 1 2.174 ms, 2 2.068, 3 2.098, 4 2.113, 6 2.156, 8 2.185 (longer runs leave a
+// longer tail at the end of the grid); per = 2 is the default (TOLCUDA_PER).
+constexpr int MAXPER = 4;
+template <int FORM, int WIND, int MAXT, int MINB, int MODE, bool LOOP>
+__global__ void __launch_bounds__(MAXT, MINB)
+fg_cta_kernel(const __grid_constant__ FgConst c, int B, int per_arg, const double *__restrict__ x, long ldx,
+               double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG,
+               double *__restrict__ S, long ldS) {
     constexpr bool SUMM = (MODE == MODE_SUMMARY);
     extern __shared__ __align__(16) double smem[];
-    __shared__ double red[SUMM ? 4 : 2][32];
-    __shared__ int arrivals;
+    __shared__ double red[MAXPER][SUMM ? 4 : 2][32];
+    __shared__ int arrivals[MAXPER];
     const int ts = c.ts;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    double *sx = smem + (size_t)warp * WARP_SMEM;
-    double *tile = sx + SX_LEN;
-    const size_t b = blockIdx.x;
-    const double *xb = x + b * ldx;
-    double *Fb = F + b * ldF;
-    double *Gb = G + b * ldG;
-
-    // stage this warp's x slice: doubles [11*k0, 11*k0 + 1 + 11*(nk+1)) of the trajectory
+    const int tid = thread_index();
+    const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    // LOOP = false is the straight-line instance for runs of one trajectory (small batches): ptxas then
+    // hoists the address arithmetic the loop form has to re-derive per trajectory (7 % fewer instructions)
+    const int per = LOOP ? per_arg : 1;
+    const int nslice = per > 1 ? 2 : 1;  // slice buffers per warp (the host sizes the dynamic shared memory alike)
+    double *wsm = smem + (size_t)warp * (nslice * SX_LEN + TILE_LEN);
+    double *tile = wsm + nslice * SX_LEN;
+    const uint32_t wsm_s = smem_addr(wsm), tile_s = wsm_s + 8 * nslice * SX_LEN;
+    const size_t b0 = (size_t)per * blockIdx.x;
+    const int ntraj = LOOP ? (int)min((size_t)per, (size_t)B - b0) : 1;
     const int k0 = 32 * warp;
     const int nk = min(32, ts - k0);
-    slice_prefetch(sx, xb + (size_t)PX * k0, 1 + PX * (nk + 1), lane);
+    const int cnt = 1 + PX * (nk + 1);           // doubles of a slice
+    const double *xw = x + b0 * ldx + (size_t)PX * k0;  // this warp's slice of the run's first trajectory
+    slice_prefetch(wsm_s, xw, cnt, lane);
     cp_async_commit();
-    const double dt = __ldg(xb);
-    double n0 = 0.0, ne = 0.0;  // node 0 / node ts, for whichever warp ends up running the epilogue
+    // dt, node 0 and node ts of a trajectory are requested one trajectory ahead, like its slice
+    double dt_nx = __ldg(xw - (size_t)PX * k0), n0_nx = 0.0, ne_nx = 0.0;
     if (lane < PX) {
-        n0 = __ldg(xb + 1 + lane);
-        ne = __ldg(xb + (size_t)PX * ts + 1 + lane);
+        n0_nx = __ldg(xw - (size_t)PX * k0 + 1 + lane);
+        ne_nx = __ldg(xw - (size_t)PX * k0 + (size_t)PX * ts + 1 + lane);
     }
     if (needG) tile_init(tile, lane);
-    if (threadIdx.x == 0) arrivals = 0;
+    if (tid < MAXPER) arrivals[tid] = 0;
     __syncthreads();
+#pragma unroll 1
+    for (int t = 0; t < ntraj; t++) {
+        const size_t b = b0 + t;
+        const int slot = t & 1;
+        const double dt = dt_nx, n0 = n0_nx, ne = ne_nx;
+        // the next trajectory's slice goes to the other buffer (whose previous user, trajectory t-1, is done)
+        if (t + 1 < ntraj) {
+            const double *xn = xw + (t + 1) * ldx;
+            slice_prefetch(wsm_s + 8 * (slot ^ 1) * SX_LEN, xn, cnt, lane);
+            dt_nx = __ldg(xn - (size_t)PX * k0);
+            if (lane < PX) {
+                n0_nx = __ldg(xn - (size_t)PX * k0 + 1 + lane);
+                ne_nx = __ldg(xn - (size_t)PX * k0 + (size_t)PX * ts + 1 + lane);
+            }
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        double *Fb = F + b * ldF, *Gb = G + b * ldG;
+        TileSums tsum;
+        tile_eval<FORM, WIND, MODE>(c, wsm + slot * SX_LEN, tile, tile_s, dt, k0, nk, lane, Fb, Gb, needF, needG, tsum);
+        __syncwarp();
+        const double sumT = warp_sum(tsum.sumT);
+        const double sump = FORM == TOLCUDA_FORM_S10 ? warp_sum(tsum.sump) : 0.0;
+        const double wdmax = SUMM ? warp_max(tsum.dmax) : 0.0, wdssq = SUMM ? warp_sum(tsum.dssq) : 0.0;
+        int last = 0;
+        if (lane == 0) {
+            red[t][0][warp] = sumT;
+            red[t][1][warp] = sump;
+            if (SUMM) {
+                red[t][SUMM ? 2 : 0][warp] = wdmax;
+                red[t][SUMM ? 3 : 0][warp] = wdssq;
+            }
+            __threadfence_block();
+            last = (atomicAdd(&arrivals[t], 1) == nwarps - 1);
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            __threadfence_block();
+            const volatile double *vred = &red[t][0][0];
+            double tT = 0.0, tp = 0.0, dmax = 0.0, dssq = 0.0;
+            for (int w = 0; w < nwarps; w++) {  // fixed order: deterministic
+                tT += vred[w];
+                tp += vred[32 + w];
+                if (SUMM) {
+                    dmax = fmax(dmax, vred[64 + w]);
+                    dssq += vred[96 + w];
+                }
+            }
+            traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG, dmax, dssq,
+                                SUMM ? S + b * ldS : nullptr, MODE == MODE_COMPACT ? NVAR : REC);
+        }
+    }
     cp_async_wait<0>();
-    __syncwarp();
-
-    TileSums tsum;
-    tile_eval<FORM, WIND, MODE>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, tsum);
-
-    // cost sums: warp shuffle, then across warps through shared memory
-    const double sumT = warp_sum(tsum.sumT);
-    const double sump = FORM == TOLCUDA_FORM_S10 ? warp_sum(tsum.sump) : 0.0;
-    const double wdmax = SUMM ? warp_max(tsum.dmax) : 0.0, wdssq = SUMM ? warp_sum(tsum.dssq) : 0.0;
-    int last = 0;
-    if (lane == 0) {
-        red[0][warp] = sumT;
-        red[1][warp] = sump;
-        if (SUMM) {
-            red[SUMM ? 2 : 0][warp] = wdmax;
-            red[SUMM ? 3 : 0][warp] = wdssq;
-        }
-        __threadfence_block();
-        last = (atomicAdd(&arrivals, 1) == nwarps - 1);
-    }
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (!last) return;
-    __threadfence_block();
-    const volatile double *vred = &red[0][0];
-    double tT = 0.0, tp = 0.0, dmax = 0.0, dssq = 0.0;
-    for (int w = 0; w < nwarps; w++) {  // fixed order: deterministic
-        tT += vred[w];
-        tp += vred[32 + w];
-        if (SUMM) {
-            dmax = fmax(dmax, vred[64 + w]);
-            dssq += vred[96 + w];
-        }
-    }
-    traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG, dmax, dssq, SUMM ? S + b * ldS : nullptr,
-                        MODE == MODE_COMPACT ? NVAR : REC);
-}
-
-template <int FORM, int WIND, int MAXT, int MINB, int MODE>
-__global__ void __launch_bounds__(MAXT, MINB)
-fg_cta_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, long ldx,
-              double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG,
-              double *__restrict__ S, long ldS) {
-    fg_cta_body<FORM, WIND, MODE>(c, x, ldx, F, ldF, G, ldG, needF, needG, S, ldS);
 }
 
 // ---- kernel B: persistent warps, one trajectory per warp at a time ------------------------------------------
@@ -816,14 +849,16 @@ fg_warp_kernel(const __grid_constant__ FgConst c, int B, const double *__restric
     extern __shared__ __align__(16) double smem[];
     const int ts = c.ts;
     const int nt = (ts + 31) >> 5;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = thread_index();
+    const int lane = tid & 31, warp = tid >> 5;
     double *wsm = smem + (size_t)warp * WARP_SMEM_B;
     double *tile = wsm + 2 * SX_LEN;
+    const uint32_t wsm_s = smem_addr(wsm), tile_s = wsm_s + 8 * 2 * SX_LEN;
     const int total = gridDim.x * WARPS;
     int b = blockIdx.x * WARPS + warp, t = 0, buf = 0;
     if (b >= B) return;
 
-    slice_prefetch(wsm, x + (size_t)b * ldx, 1 + PX * (min(32, ts) + 1), lane);
+    slice_prefetch(wsm_s, x + (size_t)b * ldx, 1 + PX * (min(32, ts) + 1), lane);
     cp_async_commit();
     if (needG) tile_init(tile, lane);
     double dt = 0.0, n0 = 0.0, accT = 0.0, accp = 0.0, accm = 0.0, accq = 0.0;
@@ -837,7 +872,7 @@ fg_warp_kernel(const __grid_constant__ FgConst c, int B, const double *__restric
         double *sx = wsm + buf * SX_LEN;  // current slice; the other one receives the prefetch
         if (nb < B) {
             const int nk2 = min(32, ts - 32 * ntile);
-            slice_prefetch(wsm + (buf ^ 1) * SX_LEN, x + (size_t)nb * ldx + (size_t)PX * 32 * ntile,
+            slice_prefetch(wsm_s + 8 * (buf ^ 1) * SX_LEN, x + (size_t)nb * ldx + (size_t)PX * 32 * ntile,
                            1 + PX * (nk2 + 1), lane);
         }
         cp_async_commit();
@@ -852,7 +887,7 @@ fg_warp_kernel(const __grid_constant__ FgConst c, int B, const double *__restric
         const double ne = (t == nt - 1 && lane < PX) ? sx[1 + PX * nk + lane] : 0.0;
         double *Fb = F + (size_t)b * ldF, *Gb = G + (size_t)b * ldG;
         TileSums tsum;
-        tile_eval_call<FORM, WIND, MODE>(c, sx, tile, dt, k0, nk, lane, Fb, Gb, needF, needG, tsum);
+        tile_eval_call<FORM, WIND, MODE>(c, sx, tile, tile_s, dt, k0, nk, lane, Fb, Gb, needF, needG, tsum);
         accT += tsum.sumT;
         accp += tsum.sump;
         accm = fmax(accm, tsum.dmax);
@@ -873,11 +908,11 @@ fg_warp_kernel(const __grid_constant__ FgConst c, int B, const double *__restric
     cp_async_wait<0>();
 }
 
-template <int FORM, int WIND, int MAXT, int MINB, int MODE>
-cudaError_t launch_cta(const FgLaunch &L) {
-    auto kern = fg_cta_kernel<FORM, WIND, MAXT, MINB, MODE>;
+template <int FORM, int WIND, int MAXT, int MINB, int MODE, bool LOOP>
+cudaError_t launch_cta_as(const FgLaunch &L, const int per) {
+    auto kern = fg_cta_kernel<FORM, WIND, MAXT, MINB, MODE, LOOP>;
     const int nthr = 32 * ((L.c->ts + 31) / 32);
-    const size_t smem = sizeof(double) * (size_t)(nthr / 32) * WARP_SMEM;
+    const size_t smem = sizeof(double) * (size_t)(nthr / 32) * ((per > 1 ? 2 : 1) * SX_LEN + TILE_LEN);
     // the attribute is per device (and this static per instantiation): tolbatch drives one device per thread
     static std::atomic<size_t> configured[MAX_DEVICES];
     std::atomic<size_t> &done = configured[L.device & (MAX_DEVICES - 1)];
@@ -886,8 +921,18 @@ cudaError_t launch_cta(const FgLaunch &L) {
         if (e != cudaSuccess) return e;
         done.store(smem, std::memory_order_release);
     }
-    kern<<<L.B, nthr, smem, L.stream>>>(*L.c, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG, L.S, L.ldS);
+    kern<<<(L.B + per - 1) / per, nthr, smem, L.stream>>>(*L.c, L.B, per, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG, L.S, L.ldS);
     return cudaGetLastError();
+}
+
+// runs of `per` trajectories per CTA pay off once the grid is many waves deep; small batches keep one
+// trajectory per CTA (more CTAs to spread over the SMs, and the cheaper straight-line instance)
+template <int FORM, int WIND, int MAXT, int MINB, int MODE>
+cudaError_t launch_cta(const FgLaunch &L) {
+    int per = L.per < 1 ? 1 : (L.per > MAXPER ? MAXPER : L.per);
+    if (L.per_auto && L.B < 48 * L.sm_count) per = 1;
+    return per == 1 ? launch_cta_as<FORM, WIND, MAXT, MINB, MODE, false>(L, 1)
+                    : launch_cta_as<FORM, WIND, MAXT, MINB, MODE, true>(L, per);
 }
 
 template <int FORM, int WIND, int WARPS, int MINB, int MODE>

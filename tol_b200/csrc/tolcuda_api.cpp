@@ -53,6 +53,8 @@ struct tolcuda_ctx {
     tolcuda_config cfg;
     FgConst c;
     int kernel = 0;
+    int per = 2;  // kernel A: trajectories per CTA for large batches (TOLCUDA_PER fixes it for every batch size)
+    int per_auto = 1;
     int zero_copy = 1;  // single-trajectory path: kernel works on the mapped pinned block (TOLCUDA_ZEROCOPY=0: staged copies)
     int sm_count = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -87,6 +89,8 @@ int launch(tolcuda_ctx *h, cudaStream_t st, int B, const double *x, long ldx, do
     L.x = x, L.ldx = ldx, L.F = F, L.ldF = ldF, L.G = G, L.ldG = ldG;
     L.needF = needF, L.needG = needG;
     L.kernel = h->kernel;
+    L.per = h->per;
+    L.per_auto = h->per_auto;
     L.sm_count = h->sm_count;
     L.device = h->cfg.device;
     L.stream = st;
@@ -232,6 +236,7 @@ int tolcuda_create(const tolcuda_config *cfg, tolcuda_handle *out) {
     pattern_build(c.form, c.ts, h->iG, h->jG);
 
     if (const char *env = std::getenv("TOLCUDA_KERNEL")) h->kernel = std::atoi(env);  // tests / tuning
+    if (const char *env = std::getenv("TOLCUDA_PER")) h->per = std::atoi(env), h->per_auto = 0;
     if (const char *env = std::getenv("TOLCUDA_ZEROCOPY")) h->zero_copy = std::atoi(env);
     if (const char *env = std::getenv("TOLCUDA_COMPACT")) h->compact_host = std::atoi(env);
 
