@@ -458,3 +458,23 @@ def test_degenerate_inputs_are_non_finite_where_the_reference_is(name, oracle_bu
         assert np.array_equal(np.isfinite(got), fin), what
         assert_parity(np.where(fin, got, 0.0), np.where(fin, ref, 0.0), name + " degenerate " + what)
     assert np.isfinite(F[[0, 5]]).all() and np.isfinite(G[[0, 5]]).all()
+
+
+@pytest.mark.parametrize("name", ["S10_tempest_ts200", "G7_skywalker_ts100", "S10_tempest_ts1"])
+@pytest.mark.parametrize("per", [1, 2, 3, 4])
+def test_runs_of_trajectories_per_cta(name, per, monkeypatch):
+    """kernel A evaluates `per` consecutive trajectories per CTA (TOLCUDA_PER; default 2 for large batches, the
+    straight-line single-trajectory instance for small ones): every run length, batch sizes that leave a
+    partial last run, and B = 1 must give the bits of the default configuration"""
+    g = load_golden(name)
+    X = T.synth.batch(g["x"][0], 777, 0, 23)
+    ev = T.Evaluator.from_golden(g)
+    Fd, Gd = ev.eval_batch_host(X, full_copy=True)
+    ev.close()
+    monkeypatch.setenv("TOLCUDA_PER", str(per))
+    ev = T.Evaluator.from_golden(g)
+    for B in (23, 22, 1):
+        F, G = ev.eval_batch_host(X[:B], full_copy=True)
+        assert np.array_equal(F.view(np.int64), Fd[:B].view(np.int64))
+        assert np.array_equal(G.view(np.int64), Gd[:B].view(np.int64))
+    ev.close()

@@ -956,7 +956,7 @@ cudaError_t launch_warp(const FgLaunch &L) {
 
 template <int FORM, int WIND, int MODE>
 cudaError_t launch_sel(const FgLaunch &L) {
-    // Kernel A (one CTA per trajectory) needs the whole trajectory in one CTA at a register budget that
+    // Kernel A (one CTA per run of trajectories) needs the whole trajectory in one CTA at a register budget that
     // does not spill: ts <= 256.  Longer trajectories, and L.kernel == 2, take kernel B, whose warps walk
     // the tiles of a trajectory one after the other (any ts).
     const int ts = L.c->ts;
