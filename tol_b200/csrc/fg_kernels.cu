@@ -753,7 +753,9 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int B, int per_arg, const doubl
     __shared__ int arrivals[MAXPER];
     const int ts = c.ts;
     const int tid = thread_index();
-    const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    // the warp index through a shuffle from lane 0: provably warp-uniform, so everything derived from it
+    // (k0, slice and record addresses, the bulk copies' operands) can live on the uniform datapath
+    const int lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), nwarps = blockDim.x >> 5;
     // LOOP = false is the straight-line instance for runs of one trajectory (small batches): ptxas then
     // hoists the address arithmetic the loop form has to re-derive per trajectory (7 % fewer instructions)
     const int per = LOOP ? per_arg : 1;
@@ -850,7 +852,7 @@ fg_warp_kernel(const __grid_constant__ FgConst c, int B, const double *__restric
     const int ts = c.ts;
     const int nt = (ts + 31) >> 5;
     const int tid = thread_index();
-    const int lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform, see kernel A
     double *wsm = smem + (size_t)warp * WARP_SMEM_B;
     double *tile = wsm + 2 * SX_LEN;
     const uint32_t wsm_s = smem_addr(wsm), tile_s = wsm_s + 8 * 2 * SX_LEN;
