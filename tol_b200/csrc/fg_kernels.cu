@@ -30,10 +30,10 @@
 // (208-byte pieces measured 4.8 TB/s against 7.5 TB/s for a plain fill).  So G leaves as whole
 // 832-byte window records, contiguous in SNOPT coordinate order:
 //   * each warp stages the 33-node slice of x its windows need in shared memory (cp.async, 16-byte);
-//   * a window's 104-value record is assembled in one of the warp's 2 x 4 record slots whose structural
-//     constants (0, +-1) are written once; per group of 4 windows only the 33 x-dependent entries are
-//     stored, and the 4 finished records (3,328 contiguous bytes) go to the TMA unit as one
-//     cp.async.bulk shared->global copy while the lanes fill the other buffer;
+//   * a window's 104-value record is assembled in one of the warp's 8 record slots whose structural
+//     constants (0, +-1) are written once per run of trajectories; per pass of 8 windows only the 33
+//     x-dependent entries are stored, and the 8 finished records (6,656 contiguous bytes) go to the TMA unit
+//     as one cp.async.bulk shared->global copy;
 //   * F (8 defects per window) and the S10 objective-row entries go out through the dead x slice as
 //     coalesced stores.  Cost sums use warp-shuffle reductions.
 #include <cuda_runtime.h>
@@ -53,16 +53,17 @@ constexpr int PF = TOLCUDA_PF;
 constexpr int REC = TOLCUDA_REC;
 // Record buffers.  A drain pass hands NPP windows (lanes NPP*g .. NPP*g+NPP-1) to the TMA unit: each of those
 // lanes places its 33 x-dependent values in its own record slot (the slots' constants are written once per
-// warp), then lane 0 issues the bulk copies, one per dense run of UNIT records.  The layout is a build-time
-// choice so that variants can be measured side by side (tools/exp/build_variant.sh); measured on B200, S10
-// ts=200, B=16,384 (profiles/r1_history.md): NPP=4 / 2 buffers / dense quads 0.558 ms; the same with padded
-// pairs (conflict-free stores, two copies per pass) 0.589; NPP=16 / 1 buffer / padded pairs 0.634;
-// NPP=16 dense 0.584; NPP=8 / 1 buffer / padded pairs 0.584.  A kernel that only moves the same bytes
-// (tools/exp/storebw.cu: x row in, F row out, G row out as 3,328-byte bulk copies, no arithmetic) takes 0.50.
+// run of trajectories), then lane 0 issues the bulk copies, one per dense run of UNIT records.  The layout is a
+// build-time choice so that variants can be measured side by side (tools/exp/build_variant.sh;
+// profiles/r1_history.md).  Default: one buffer of 8 records per warp, 4 passes per tile, one 6,656-byte
+// bulk copy per pass; a pass waits until the TMA unit has read the previous one.  Against two buffers of 4
+// records (8 passes, fill and read overlapped) this halves the shared-store instructions, proxy fences and
+// warp barriers of a tile for the same shared memory, and measured 0.3 % faster; 16-record buffers would
+// leave room for only one CTA per SM.
 #ifndef TOLCUDA_NPP
-#define TOLCUDA_NPP 4
-#define TOLCUDA_NBUF 2
-#define TOLCUDA_UNIT 4
+#define TOLCUDA_NPP 8
+#define TOLCUDA_NBUF 1
+#define TOLCUDA_UNIT 8
 #define TOLCUDA_PADW 0
 #endif
 constexpr int NPP = TOLCUDA_NPP;       // windows per drain pass
