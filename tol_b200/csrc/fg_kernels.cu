@@ -622,16 +622,6 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
     }
 }
 
-// Out-of-line instance for the persistent kernel: inlined into its trajectory/tile loop, ptxas keeps
-// dozens of extra values live across the loop and spills; as a call the tile body is allocated on its own.
-template <int FORM, int WIND, int MODE>
-__device__ __noinline__ void tile_eval_call(const FgConst &c, double *sx, double *tile, const uint32_t tile_s, const double dt,
-                                            const int k0, const int nk, const int lane,
-                                            double *__restrict__ Fb, double *__restrict__ Gb,
-                                            const int needF, const int needG, TileSums &ts_out) {
-    tile_eval<FORM, WIND, MODE>(c, sx, tile, tile_s, dt, k0, nk, lane, Fb, Gb, needF, needG, ts_out);
-}
-
 // ---- end of a trajectory: F[0], boundary rows, objective-row ends --------------------------------------
 //
 // Executed by one whole warp.  tT, tp: the trajectory's cost sums; n0 / ne: lane c < 11 holds state c of
@@ -842,7 +832,8 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int B, int per_arg, const doubl
 // Every warp walks trajectories b = warp_id, warp_id + total_warps, ... and, within a trajectory, its
 // tiles in order, so cost sums stay in registers and no warp ever waits for another.  While a tile is
 // evaluated, the x slice of the next tile (or of the next trajectory's first tile) is already in flight
-// (cp.async) into the other slice buffer.  Selectable variant (TOLCUDA_KERNEL=2).
+// (cp.async) into the other slice buffer.  Serves trajectories longer than 256 windows (any ts), and every
+// trajectory with TOLCUDA_KERNEL=2; 0.82 of the roofline on S10 ts=200 against kernel A's 0.98.
 template <int FORM, int WIND, int WARPS, int MINB, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 fg_warp_kernel(const __grid_constant__ FgConst c, int B, const double *__restrict__ x, long ldx,
@@ -890,7 +881,7 @@ fg_warp_kernel(const __grid_constant__ FgConst c, int B, const double *__restric
         const double ne = (t == nt - 1 && lane < PX) ? sx[1 + PX * nk + lane] : 0.0;
         double *Fb = F + (size_t)b * ldF, *Gb = G + (size_t)b * ldG;
         TileSums tsum;
-        tile_eval_call<FORM, WIND, MODE>(c, sx, tile, tile_s, dt, k0, nk, lane, Fb, Gb, needF, needG, tsum);
+        tile_eval<FORM, WIND, MODE>(c, sx, tile, tile_s, dt, k0, nk, lane, Fb, Gb, needF, needG, tsum);
         accT += tsum.sumT;
         accp += tsum.sump;
         accm = fmax(accm, tsum.dmax);
