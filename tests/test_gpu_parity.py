@@ -478,3 +478,48 @@ def test_runs_of_trajectories_per_cta(name, per, monkeypatch):
         assert np.array_equal(F.view(np.int64), Fd[:B].view(np.int64))
         assert np.array_equal(G.view(np.int64), Gd[:B].view(np.int64))
     ev.close()
+
+
+def test_api_misuse_is_reported_not_executed():
+    """error behaviour of the C ABI on a live device: bad arguments come back as TOLCUDA_E* codes with a
+    message, nothing is written, and the callback turns a mismatching problem size into Status = -2"""
+    import ctypes as C
+    g = load_golden("S10_tempest_ts100")
+    ev = T.Evaluator.from_golden(g)
+    L = ev.L
+    x = np.ascontiguousarray(g["x"][0])
+    F = np.full(ev.neF, np.nan)
+    G = np.full(ev.neG, np.nan)
+    dp = C.POINTER(C.c_double)
+    assert L.tolcuda_eval(ev.h, None, 1, F.ctypes.data_as(dp), 1, G.ctypes.data_as(dp)) == -1      # EINVAL
+    assert L.tolcuda_eval(ev.h, x.ctypes.data_as(dp), 1, None, 0, None) == -1
+    assert L.tolcuda_eval(ev.h, x.ctypes.data_as(dp), 0, None, 0, None) == 0                        # nothing asked
+    # leading dimension shorter than a row, negative batch, summary with too small a stride
+    flags = T.evaluator.NEED_F | T.evaluator.NEED_G | T.evaluator.HOST_PTRS
+    assert L.tolcuda_eval_batch(ev.h, 1, x.ctypes.data, ev.n - 1, F.ctypes.data, ev.neF, G.ctypes.data, ev.neG, flags) == -1
+    assert b"leading dimension" in L.tolcuda_last_error()
+    assert L.tolcuda_eval_batch(ev.h, -1, x.ctypes.data, ev.n, F.ctypes.data, ev.neF, G.ctypes.data, ev.neG, flags) == -1
+    assert L.tolcuda_eval_batch(ev.h, 0, None, 0, None, 0, None, 0, flags) == 0                     # empty batch
+    S = np.zeros(4)
+    assert L.tolcuda_eval_batch_summary(ev.h, 1, x.ctypes.data, ev.n, F.ctypes.data, ev.neF, G.ctypes.data, ev.neG,
+                                        S.ctypes.data, 3, flags) == -1
+    assert L.tolcuda_eval_batch_summary(ev.h, 1, x.ctypes.data, ev.n, F.ctypes.data, ev.neF, G.ctypes.data, ev.neG,
+                                        S.ctypes.data, 4, flags | T.evaluator.COMPACT_G) == -2     # EUNSUPPORTED
+    assert np.isnan(F).all() and np.isnan(G).all()
+    # unsupported configurations never reach the device
+    cfg = T.make_config("S10", 100, g["ac"], g["gn"], g["goal_ned"])
+    h = C.c_void_p()
+    for field, bad in (("formulation", 3), ("ts", 0), ("wind_model", 2)):
+        c2 = T.make_config("S10", 100, g["ac"], g["gn"], g["goal_ned"])
+        setattr(c2, field, bad)
+        assert L.tolcuda_create(C.byref(c2), C.byref(h)) == -2 and not h.value
+    assert L.tolcuda_create(C.byref(cfg), None) == -1
+    # the callback with another problem's sizes: Status = -2 (SNOPT: terminate), arrays untouched
+    L.tolcuda_bind_global(ev.h)
+    st = C.c_int(0)
+    ints = [C.c_int(v) for v in (ev.n + 11, 1, ev.neF, 1, ev.neG, 0, 0, 0)]
+    L.DEFINEGusrfg_(C.byref(st), C.byref(ints[0]), x.ctypes.data_as(dp), C.byref(ints[1]), C.byref(ints[2]),
+                    F.ctypes.data_as(dp), C.byref(ints[3]), C.byref(ints[4]), G.ctypes.data_as(dp), None,
+                    C.byref(ints[5]), None, C.byref(ints[6]), None, C.byref(ints[7]))
+    assert st.value == -2 and np.isnan(F).all() and np.isnan(G).all()
+    ev.close()
