@@ -167,6 +167,11 @@ int tolcuda_eval_batch(tolcuda_handle h, int B, const double *x, long ldx, doubl
 long tolcuda_compact_len(int formulation, int ts);
 int tolcuda_expand_compact_g(int formulation, int ts, long B, const double *Gc, long ldGc, double *G, long ldG,
                              int threads);
+/* The same expansion on the device (expand_kernel.cu): B compact rows in device memory -> rows in coordinate
+ * order in device memory, on the context's stream; bit-identical to what tolcuda_eval_batch writes without
+ * TOLCUDA_COMPACT_G.  flags: 0 or TOLCUDA_NO_SYNC.  For results kept or gathered in compact form on the GPU. */
+int tolcuda_expand_compact_g_device(tolcuda_handle h, long B, const double *Gc, long ldGc, double *G, long ldG,
+                                    int flags);
 /* host threads the host-pointer batch path of this context expands compact rows with (0 = default:
  * environment TOLCUDA_HOST_THREADS, else the cores available to the process / LOCAL_WORLD_SIZE) */
 int tolcuda_set_host_threads(tolcuda_handle h, int threads);

@@ -141,6 +141,14 @@ def test_compact_rows_path_equals_full_rows(name, kernel, monkeypatch):
     Gdh = Gd.cpu().numpy()
     assert np.array_equal(Gdh[:, :ev.compact_len].view(np.int64), Gr.view(np.int64)) and np.isnan(Gdh[:, ev.compact_len:]).all()
     assert np.array_equal(Fd.cpu().numpy().view(np.int64), Ff.view(np.int64))
+    # expansion on the device (expand_kernel.cu): aligned rows (16-byte stores) and rows shifted by 8 bytes
+    for ld, off in ((T.evaluator.padded_ld(ev.neG), 0), (ev.neG + 3, 1)):
+        Gx = torch.full((B * ld + 8,), float("nan"), dtype=torch.float64, device="cuda")
+        Gv = Gx[off:off + B * ld].view(B, ld)
+        ev.expand_compact_device(Gd, Gv)
+        Gxh = Gv.cpu().numpy()
+        assert np.array_equal(np.ascontiguousarray(Gxh[:, :ev.neG]).view(np.int64), Gf.view(np.int64))
+        assert np.isnan(Gxh[:, ev.neG:]).all()
     ev.close()
 
 
@@ -523,3 +531,51 @@ def test_api_misuse_is_reported_not_executed():
                     C.byref(ints[5]), None, C.byref(ints[6]), None, C.byref(ints[7]))
     assert st.value == -2 and np.isnan(F).all() and np.isnan(G).all()
     ev.close()
+
+
+def _nccl_gather_worker(rank, world, port, name, B, out_path):
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    import tol_b200.dist as D
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    g = load_golden(name)
+    ev = T.Evaluator.from_golden(g, device=rank)
+    b0, b1 = D.my_shard(B)
+    X = torch.from_numpy(T.synth.batch(g["x"][0], 2718, b0, b1)).cuda()
+    F, G = D.eval_and_gather_device(ev, X, B, dst=0)
+    if rank == 0:
+        np.savez(out_path, F=F.cpu().numpy(), G=G.cpu().numpy())
+    dist.barrier()
+    ev.close()
+    dist.destroy_process_group()
+
+
+def test_shards_gathered_on_one_gpu_over_nccl(tmp_path):
+    """2+ GPUs: every rank evaluates its shard into COMPACT G rows, the shards are gathered on GPU 0 with one
+    NCCL gather per array (a third of the bytes of full rows) and expanded there by expand_kernel.cu; the
+    result must be bit-identical to one GPU evaluating the whole batch into full rows"""
+    import socket
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    name, B = "S10_tempest_ts100", 37
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "gathered.npz")
+    mp.spawn(_nccl_gather_worker, args=(2, port, name, B, out), nprocs=2, join=True)
+    got = np.load(out)
+    g = load_golden(name)
+    ev = T.Evaluator.from_golden(g)
+    F, G = ev.eval_batch_host(T.synth.batch(g["x"][0], 2718, 0, B), full_copy=True)
+    ev.close()
+    assert np.array_equal(got["F"].view(np.int64), F.view(np.int64))
+    assert np.array_equal(got["G"].view(np.int64), G.view(np.int64))

@@ -33,4 +33,8 @@ struct FgLaunch {
 // enqueue one batched F/G evaluation; device pointers
 cudaError_t fg_launch(const FgLaunch &L);
 
+// enqueue the expansion of B compact G rows into rows in coordinate order (expand_kernel.cu); device pointers
+cudaError_t expand_launch(int form, int ts, int R0, int nbG, long B, const double *Gc, long ldGc, double *G,
+                          long ldG, cudaStream_t stream);
+
 #endif

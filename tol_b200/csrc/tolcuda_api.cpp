@@ -604,6 +604,22 @@ int tolcuda_expand_compact_g(int formulation, int ts, long B, const double *Gc, 
     return 0;
 }
 
+int tolcuda_expand_compact_g_device(tolcuda_handle h, long B, const double *Gc, long ldGc, double *G, long ldG,
+                                    int flags) {
+    if (!h || B < 0) return TOLCUDA_EINVAL;
+    const FgConst &c = h->c;
+    if (B > 0 && (!Gc || !G || ldGc < compact_len(c.form, c.ts) || ldG < c.neG)) {
+        set_error("tolcuda_expand_compact_g_device: null pointer or leading dimension shorter than the row");
+        return TOLCUDA_EINVAL;
+    }
+    CU(cudaSetDevice(h->cfg.device));
+    cudaError_t e = expand_launch(c.form, c.ts, c.R0, c.nbG, B, Gc, ldGc, G, ldG, h->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "expand_launch");
+    h->launches += B > 0 ? (B + 65534) / 65535 : 0;
+    if (!(flags & TOLCUDA_NO_SYNC)) CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 int tolcuda_set_host_threads(tolcuda_handle h, int threads) {
     if (!h || threads < 0) return TOLCUDA_EINVAL;
     h->host_threads = threads;

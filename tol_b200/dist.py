@@ -50,3 +50,39 @@ def gather_rows(local, B):
         b0, b1 = shard_range(B, q, w)
         out[b0:b1] = parts[q].numpy()[:b1 - b0]
     return out
+
+
+def eval_and_gather_device(ev, X, B, dst=0):
+    """Device-side gather: every rank evaluates its shard X (torch CUDA tensor
+    [b1-b0, >= n]) into F rows and COMPACT G rows, the shards are gathered on GPU `dst` with one NCCL gather
+    per array -- G crosses NVLink as compact rows, a third of the bytes -- and expanded there into rows in
+    coordinate order by the device expansion kernel.  Returns (F [B, neF], G [B, neG]) as CUDA tensors on rank
+    `dst`, (None, None) elsewhere; rows are placed by trajectory index."""
+    r, w = world()
+    nb = X.shape[0]
+    per = (B + w - 1) // w
+    Lc = ev.compact_len
+    Fl = torch.zeros(per, ev.neF, dtype=torch.float64, device=X.device)
+    Gl = torch.zeros(per, Lc, dtype=torch.float64, device=X.device)
+    if nb:
+        ev.eval_batch_device(X, Fl[:nb], Gl[:nb], compact_rows=True)
+    if w == 1:
+        G = torch.empty(B, ev.neG, dtype=torch.float64, device=X.device)
+        ev.expand_compact_device(Gl[:B], G)
+        return Fl[:B], G
+    Fp = [torch.empty_like(Fl) for _ in range(w)] if r == dst else None
+    Gp = [torch.empty_like(Gl) for _ in range(w)] if r == dst else None
+    dist.gather(Fl, Fp, dst=dst)
+    dist.gather(Gl, Gp, dst=dst)
+    if r != dst:
+        return None, None
+    torch.cuda.current_stream().synchronize()  # the gathers ran on torch's stream, the expansion runs on the context's
+    F = torch.empty(B, ev.neF, dtype=torch.float64, device=X.device)
+    G = torch.empty(B, ev.neG, dtype=torch.float64, device=X.device)
+    for q in range(w):
+        b0, b1 = shard_range(B, q, w)
+        if b1 > b0:
+            F[b0:b1] = Fp[q][:b1 - b0]
+            ev.expand_compact_device(Gp[q][:b1 - b0], G[b0:b1], sync=False)
+    ev.synchronize()
+    return F, G

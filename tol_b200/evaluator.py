@@ -222,6 +222,12 @@ class Evaluator:
         _l.check(self.L.tolcuda_eval_batch(self.h, B, X.data_ptr(), X.stride(0), F.data_ptr(), F.stride(0),
                                            G.data_ptr(), G.stride(0), flags))
 
+    def expand_compact_device(self, Gc, G, sync=True):
+        """tolcuda_expand_compact_g_device: compact rows (torch CUDA tensor [B, >= compact_len]) -> rows in
+        coordinate order (torch CUDA tensor [B, >= neG]) on the context's stream"""
+        _l.check(self.L.tolcuda_expand_compact_g_device(self.h, Gc.shape[0], Gc.data_ptr(), Gc.stride(0), G.data_ptr(),
+                                                        G.stride(0), 0 if sync else NO_SYNC))
+
     def summary_host(self, X, needF=False, needG=False):
         """tolcuda_eval_batch_summary with host arrays: [B, 4] = objective, max|defect|, max boundary
         violation, sum defect^2 (F and G are not produced unless asked for)"""
