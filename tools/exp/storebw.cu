@@ -51,68 +51,39 @@ __global__ void store_kernel(char *out, long row_bytes, int S, int mode, int sme
 // the real traffic mix of one S10 ts=200 trajectory per CTA: read the x row (cp.async, waited for), write the F
 // row (8-byte lane stores), write the G row as TMA bulk copies of S bytes; no arithmetic
 __global__ void mix_kernel(char *out, long row_bytes, const double *x, long ldx, int nx, double *F, long ldF, int nF, int S,
-                           int smem_bytes, int wait_x, int do_x, int fmode) {
+                           int smem_bytes, int wait_x, int do_x, int fmode, int rows_per_cta, int B) {
     extern __shared__ __align__(128) char sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int per = (smem_bytes / nw) & ~127;
     char *mine = sm + (long)warp * per;
-    // x slice of this warp: 364 doubles at 352*warp
-    const double *xs = x + (long)blockIdx.x * ldx + 352 * warp;
-    const int cnt = min(364, nx - 352 * warp);
-    if (do_x == 2) {  // one TMA bulk load per warp, completion on the warp's mbarrier
-        __shared__ __align__(8) unsigned long long bars[8];
-        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bars[warp]);
-        if (lane == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            const int bytes = (cnt & ~1) * 8;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             (uint32_t)__cvta_generic_to_shared(mine)),
-                         "l"(xs), "r"(bytes), "r"(bar)
-                         : "memory");
-        }
+    for (int rr = 0; rr < rows_per_cta; rr++) {
+        const long rowi = (long)blockIdx.x * rows_per_cta + rr;
+        if (rowi >= B) break;
+        const double *xs = x + rowi * ldx + 352 * warp;
+        const int cnt = min(364, nx - 352 * warp);
+        if (do_x) for (int i = lane * 2; i + 1 < cnt; i += 64)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(mine + 8 * i)), "l"(xs + i));
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
-        uint32_t done = 0;
-        while (!done)
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
-    } else if (do_x) for (int i = lane * 2; i + 1 < cnt; i += 64)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(mine + 8 * i)), "l"(xs + i));
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    if (wait_x) asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
-    double acc = wait_x ? reinterpret_cast<double *>(mine)[lane] : 1.0;
-    // F: 256 doubles per warp
-    double *Fb = F + (long)blockIdx.x * ldF + 1 + 256 * warp;
-    const int nf = min(256, nF - 1 - 256 * warp);
-    if (fmode == 1) {
-        for (int i = lane; i < nf; i += 32) Fb[i] = acc;
-    } else if (fmode == 2 && nf > 2) {  // aligned interior as one bulk copy, the two edge values by lanes
+        double acc = reinterpret_cast<double *>(mine)[lane];
+        double *Fb = F + rowi * ldF + 1 + 256 * warp;
+        const int nf = min(256, nF - 1 - 256 * warp);
+        if (fmode) for (int i = lane; i < nf; i += 32) Fb[i] = acc;
+        __syncwarp();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0) {
-            Fb[0] = acc;
-            bulk_store(Fb + 1, mine, ((nf - 1) & ~1) * 8);
-        }
-        if (lane == 1 && ((nf - 1) & 1)) Fb[nf - 1] = acc;
-    }
-    if (!wait_x) asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-    char *row = out + (long)blockIdx.x * row_bytes;
-    const long npieces = row_bytes / S;
-    const int slots = per / S;
-    int it = 0;
-    for (long p0 = (long)warp * 8; p0 < npieces; p0 += (long)nw * 8)
-        for (int q = 0; q < 8 && p0 + q < npieces; q++, it++) {
-            if (lane == 0) {
-                bulk_store(row + (p0 + q) * S, mine + (long)(it % slots) * S, S);
-                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        char *row = out + rowi * row_bytes;
+        const long npieces = row_bytes / S;
+        for (long p0 = (long)warp * 4; p0 < npieces; p0 += (long)nw * 4)
+            for (int q = 0; q < 4 && p0 + q < npieces; q++) {
+                if (lane == 0) {
+                    bulk_store(row + (p0 + q) * S, mine + 4096, S);
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+                __syncwarp();
             }
-            __syncwarp();
-        }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
 }
 
 int main(int argc, char **argv) {
@@ -159,21 +130,21 @@ int main(int argc, char **argv) {
         CK(cudaMalloc(&x, ldx * 8 * B));
         CK(cudaMalloc(&F, ldF * 8 * B));
         CK(cudaMemset(x, 0, ldx * 8 * B));
-        for (int smem_kb : {64, 100})
-            for (int S : {3328})
-                for (int var = 0; var < 6; var++) {
-                    const int wait_x = 1, do_x = var == 5 ? 2 : (var != 1 && var != 3), fmode = var == 2 || var == 3 ? 0 : (var == 4 ? 2 : 1);  // var 5: x through one TMA bulk load per warp
+        for (int smem_kb : {88})
+            for (int S : {3328, 6656})
+                for (int rpc = 1; rpc <= 2; rpc++) {
+                    const int wait_x = 1, do_x = 1, fmode = 1;
                     const int smem = smem_kb * 1024;
                     CK(cudaFuncSetAttribute(mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                    for (int i = 0; i < 2; i++) mix_kernel<<<B, 224, smem>>>(out, row, x, ldx, nx, F, ldF, nF, S, smem, wait_x, do_x, fmode);
+                    for (int i = 0; i < 2; i++) mix_kernel<<<(B + rpc - 1) / rpc, 224, smem>>>(out, row, x, ldx, nx, F, ldF, nF, S, smem, wait_x, do_x, fmode, rpc, B);
                     CK(cudaEventRecord(e0));
-                    for (int i = 0; i < 5; i++) mix_kernel<<<B, 224, smem>>>(out, row, x, ldx, nx, F, ldF, nF, S, smem, wait_x, do_x, fmode);
+                    for (int i = 0; i < 5; i++) mix_kernel<<<(B + rpc - 1) / rpc, 224, smem>>>(out, row, x, ldx, nx, F, ldF, nF, S, smem, wait_x, do_x, fmode, rpc, B);
                     CK(cudaEventRecord(e1));
                     CK(cudaEventSynchronize(e1));
                     float ms;
                     CK(cudaEventElapsedTime(&ms, e0, e1));
                     const double bytes = ((double)(row / S) * S + 8.0 * ((do_x ? nx : 0) + (fmode ? nF : 0))) * B;
-                    printf("mix  S=%5d warps/CTA= 7 smem=%3dKB x=%d F=%d: %.3f ms  %.0f GB/s (F: 1 lane stores, 2 bulk)\n", S, smem_kb, do_x, fmode, ms / 5,
+                    printf("mix  S=%5d warps/CTA= 7 smem=%3dKB rows/CTA=%d: %.3f ms  %.0f GB/s (x in, F out, G out)\n", S, smem_kb, rpc, ms / 5,
                            bytes / (ms / 5 * 1e-3) / 1e9);
                 }
     }
