@@ -66,31 +66,44 @@ inline double rec_val(const double *v, const double mdt) {
     else return mdt;
 }
 
-inline void nt1(double *p, double v) {
-    long long bits;
-    __builtin_memcpy(&bits, &v, 8);
-    _mm_stream_si64(reinterpret_cast<long long *>(p), bits);
+// NT = true: non-temporal stores (batch path: the rows are not read back by this library and are far larger than
+// the caches); NT = false: ordinary stores (single-trajectory callback: SNOPT reads G right away)
+template <bool NT>
+inline void put1(double *p, double v) {
+    if (NT) {
+        long long bits;
+        __builtin_memcpy(&bits, &v, 8);
+        _mm_stream_si64(reinterpret_cast<long long *>(p), bits);
+    } else {
+        *p = v;
+    }
+}
+template <bool NT>
+inline void put2(double *p, __m128d v) {
+    if (NT) _mm_stream_pd(p, v);
+    else _mm_storeu_pd(p, v);
 }
 
 // one record, destination 16-byte aligned: 52 streaming 16-byte stores of straight-line code
-template <int... P>
+template <bool NT, int... P>
 inline void record_aligned(double *dst, const double *v, const double mdt, std::integer_sequence<int, P...>) {
-    (_mm_stream_pd(dst + 2 * P, _mm_set_pd(rec_val<2 * P + 1>(v, mdt), rec_val<2 * P>(v, mdt))), ...);
+    (put2<NT>(dst + 2 * P, _mm_set_pd(rec_val<2 * P + 1>(v, mdt), rec_val<2 * P>(v, mdt))), ...);
 }
 // destination 8 mod 16: one 8-byte store, 51 pairs shifted by one, one 8-byte store
-template <int... P>
+template <bool NT, int... P>
 inline void record_shifted(double *dst, const double *v, const double mdt, std::integer_sequence<int, P...>) {
-    nt1(dst, rec_val<0>(v, mdt));
-    (_mm_stream_pd(dst + 1 + 2 * P, _mm_set_pd(rec_val<2 * P + 2>(v, mdt), rec_val<2 * P + 1>(v, mdt))), ...);
-    nt1(dst + REC - 1, rec_val<REC - 1>(v, mdt));
+    put1<NT>(dst, rec_val<0>(v, mdt));
+    (put2<NT>(dst + 1 + 2 * P, _mm_set_pd(rec_val<2 * P + 2>(v, mdt), rec_val<2 * P + 1>(v, mdt))), ...);
+    put1<NT>(dst + REC - 1, rec_val<REC - 1>(v, mdt));
 }
 
-// streaming copy of cnt doubles to any 8-byte aligned destination
-inline void nt_copy(double *dst, const double *src, long cnt) {
+// copy of cnt doubles to any 8-byte aligned destination
+template <bool NT>
+inline void copy_out(double *dst, const double *src, long cnt) {
     long i = 0;
-    if ((reinterpret_cast<uintptr_t>(dst) & 15) && cnt > 0) nt1(dst, src[0]), i = 1;
-    for (; i + 1 < cnt; i += 2) _mm_stream_pd(dst + i, _mm_loadu_pd(src + i));
-    if (i < cnt) nt1(dst + i, src[i]);
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) && cnt > 0) put1<NT>(dst, src[0]), i = 1;
+    for (; i + 1 < cnt; i += 2) put2<NT>(dst + i, _mm_loadu_pd(src + i));
+    if (i < cnt) put1<NT>(dst + i, src[i]);
 }
 
 // ---- AVX-512 path ---------------------------------------------------------------------------------------
@@ -132,12 +145,18 @@ inline double rec_val_rt(int pos, const double *&v, const double mdt) {
 
 // records of one row: dst = first record (8-byte aligned, Q doubles before the next 64-byte boundary),
 // v = the row's compact window values
-template <int Q>
+template <bool NT>
+__attribute__((target("avx512f"))) inline void put8(double *p, __m512d v) {
+    if (NT) _mm512_stream_pd(p, v);
+    else _mm512_store_pd(p, v);
+}
+
+template <int Q, bool NT>
 __attribute__((target("avx512f"))) void records_avx512(double *dst, const double *v, const double mdt, const int ts) {
     constexpr const LineTab &T = Lines<Q>::tab;
     const long total = (long)REC * ts;
     long j = 0;
-    for (; j < Q && j < total; j++) nt1(dst + j, rec_val_rt((int)(j % REC), v, mdt));
+    for (; j < Q && j < total; j++) put1<NT>(dst + j, rec_val_rt((int)(j % REC), v, mdt));
     if (j == total) return;
     __m512d tm[13];
     const __m512d vm = _mm512_set1_pd(mdt);
@@ -149,32 +168,55 @@ __attribute__((target("avx512f"))) void records_avx512(double *dst, const double
     for (; i + 13 <= nlines; i += 13) {
 #pragma GCC unroll 13
         for (int l = 0; l < 13; l++) {
-            _mm512_stream_pd(out + 8 * l, _mm512_mask_expandloadu_pd(tm[l], (__mmask8)T.var[l], v));
+            put8<NT>(out + 8 * l, _mm512_mask_expandloadu_pd(tm[l], (__mmask8)T.var[l], v));
             v += T.cnt[l];
         }
         out += REC;
     }
     for (int l = 0; i < nlines; i++, l++, out += 8) {
-        _mm512_stream_pd(out, _mm512_mask_expandloadu_pd(tm[l], (__mmask8)T.var[l], v));
+        put8<NT>(out, _mm512_mask_expandloadu_pd(tm[l], (__mmask8)T.var[l], v));
         v += T.cnt[l];
     }
-    for (j = Q + 8 * nlines; j < total; j++) nt1(dst + j, rec_val_rt((int)(j % REC), v, mdt));
+    for (j = Q + 8 * nlines; j < total; j++) put1<NT>(dst + j, rec_val_rt((int)(j % REC), v, mdt));
 }
 
 // AVX-512 available and not switched off (TOLCUDA_NO_AVX512, for tests of the SSE2 path)
 bool have_avx512() { return __builtin_cpu_supports("avx512f") && !std::getenv("TOLCUDA_NO_AVX512"); }
 
+template <bool NT>
 void records_dispatch_avx512(double *dst, const double *v, const double mdt, const int ts) {
     switch ((8 - (int)((reinterpret_cast<uintptr_t>(dst) >> 3) & 7)) & 7) {
-        case 0: return records_avx512<0>(dst, v, mdt, ts);
-        case 1: return records_avx512<1>(dst, v, mdt, ts);
-        case 2: return records_avx512<2>(dst, v, mdt, ts);
-        case 3: return records_avx512<3>(dst, v, mdt, ts);
-        case 4: return records_avx512<4>(dst, v, mdt, ts);
-        case 5: return records_avx512<5>(dst, v, mdt, ts);
-        case 6: return records_avx512<6>(dst, v, mdt, ts);
-        default: return records_avx512<7>(dst, v, mdt, ts);
+        case 0: return records_avx512<0, NT>(dst, v, mdt, ts);
+        case 1: return records_avx512<1, NT>(dst, v, mdt, ts);
+        case 2: return records_avx512<2, NT>(dst, v, mdt, ts);
+        case 3: return records_avx512<3, NT>(dst, v, mdt, ts);
+        case 4: return records_avx512<4, NT>(dst, v, mdt, ts);
+        case 5: return records_avx512<5, NT>(dst, v, mdt, ts);
+        case 6: return records_avx512<6, NT>(dst, v, mdt, ts);
+        default: return records_avx512<7, NT>(dst, v, mdt, ts);
     }
+}
+
+template <bool NT>
+void expand_row_as(int form, int ts, const double *src, double *dst, bool wide) {
+    int R0, nbG;
+    pattern_dims(form, ts, nullptr, nullptr, nullptr, &R0, &nbG);
+    const double *bsrc = src + R0 + (long)NVAR * ts;
+    const double mdt = bsrc[nbG];
+    copy_out<NT>(dst, src, R0);
+    double *rec = dst + R0;
+    const double *v = src + R0;
+    if (wide) {
+        records_dispatch_avx512<NT>(rec, v, mdt, ts);
+        rec += (long)REC * ts;
+    } else if ((reinterpret_cast<uintptr_t>(rec) & 15) == 0) {
+        for (int k = 0; k < ts; k++, rec += REC, v += NVAR)
+            record_aligned<NT>(rec, v, mdt, std::make_integer_sequence<int, REC / 2>());
+    } else {
+        for (int k = 0; k < ts; k++, rec += REC, v += NVAR)
+            record_shifted<NT>(rec, v, mdt, std::make_integer_sequence<int, REC / 2 - 1>());
+    }
+    copy_out<NT>(rec, bsrc, nbG);
 }
 
 }  // namespace
@@ -188,24 +230,11 @@ long compact_len(int form, int ts) {
 void expand_row(int form, int ts, const double *src, double *dst) { expand_row(form, ts, src, dst, have_avx512()); }
 
 void expand_row(int form, int ts, const double *src, double *dst, bool wide) {
-    int R0, nbG;
-    pattern_dims(form, ts, nullptr, nullptr, nullptr, &R0, &nbG);
-    const double *bsrc = src + R0 + (long)NVAR * ts;
-    const double mdt = bsrc[nbG];
-    nt_copy(dst, src, R0);
-    double *rec = dst + R0;
-    const double *v = src + R0;
-    if (wide) {
-        records_dispatch_avx512(rec, v, mdt, ts);
-        rec += (long)REC * ts;
-    } else if ((reinterpret_cast<uintptr_t>(rec) & 15) == 0) {
-        for (int k = 0; k < ts; k++, rec += REC, v += NVAR)
-            record_aligned(rec, v, mdt, std::make_integer_sequence<int, REC / 2>());
-    } else {
-        for (int k = 0; k < ts; k++, rec += REC, v += NVAR)
-            record_shifted(rec, v, mdt, std::make_integer_sequence<int, REC / 2 - 1>());
-    }
-    nt_copy(rec, bsrc, nbG);
+    expand_row_as<true>(form, ts, src, dst, wide);
+}
+
+void expand_row_cached(int form, int ts, const double *src, double *dst) {
+    expand_row_as<false>(form, ts, src, dst, have_avx512());
 }
 
 // ---- host thread pool ----------------------------------------------------------------------------------

@@ -446,26 +446,33 @@ int tolcuda_eval(tolcuda_handle h, const double *x, int needF, double *F, int ne
     CU(cudaSetDevice(h->cfg.device));
     cudaStream_t st = h->stream;
     std::memcpy(h->h_one + h->ox, x, sizeof(double) * c.n);
+    // G crosses PCIe as a compact row (a third of the bytes) and is expanded straight into the caller's array
+    // with ordinary stores -- SNOPT reads it next (TOLCUDA_COMPACT=0: the full row is copied instead)
+    const int compact = needG > 0 && h->compact_host;
+    const long lenG = compact ? compact_len(c.form, c.ts) : (long)c.neG;
     if (h->zero_copy) {
         // One launch, no copy commands: the pinned staging block is mapped into the device's address
         // space (UVA), so the kernel reads x from it and writes F/G into it across PCIe directly.
-        int rc = launch(h, st, 1, h->h_one + h->ox, c.n, h->h_one + h->oF, c.neF, h->h_one + h->oG, c.neG,
-                        needF > 0, needG > 0);
+        int rc = launch(h, st, 1, h->h_one + h->ox, c.n, h->h_one + h->oF, c.neF, h->h_one + h->oG, lenG,
+                        needF > 0, needG > 0, nullptr, 0, compact);
         if (rc) return rc;
         CU(cudaStreamSynchronize(st));
     } else {
         CU(cudaMemcpyAsync(h->d_one + h->ox, h->h_one + h->ox, sizeof(double) * c.n, cudaMemcpyHostToDevice, st));
-        int rc = launch(h, st, 1, h->d_one + h->ox, c.n, h->d_one + h->oF, c.neF, h->d_one + h->oG, c.neG,
-                        needF > 0, needG > 0);
+        int rc = launch(h, st, 1, h->d_one + h->ox, c.n, h->d_one + h->oF, c.neF, h->d_one + h->oG, lenG,
+                        needF > 0, needG > 0, nullptr, 0, compact);
         if (rc) return rc;
         if (needF > 0)
             CU(cudaMemcpyAsync(h->h_one + h->oF, h->d_one + h->oF, sizeof(double) * c.neF, cudaMemcpyDeviceToHost, st));
         if (needG > 0)
-            CU(cudaMemcpyAsync(h->h_one + h->oG, h->d_one + h->oG, sizeof(double) * c.neG, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(h->h_one + h->oG, h->d_one + h->oG, sizeof(double) * lenG, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
     if (needF > 0) std::memcpy(F, h->h_one + h->oF, sizeof(double) * c.neF);
-    if (needG > 0) std::memcpy(G, h->h_one + h->oG, sizeof(double) * c.neG);
+    if (needG > 0) {
+        if (compact) expand_row_cached(c.form, c.ts, h->h_one + h->oG, G);
+        else std::memcpy(G, h->h_one + h->oG, sizeof(double) * c.neG);
+    }
     return 0;
 }
 

@@ -29,6 +29,7 @@ void bounds(const tolcuda_config &cfg, double *xlow, double *xupp, double *Flow,
 long compact_len(int form, int ts);
 void expand_row(int form, int ts, const double *src, double *dst);
 void expand_row(int form, int ts, const double *src, double *dst, bool wide);  // wide: AVX-512 line stores
+void expand_row_cached(int form, int ts, const double *src, double *dst);     // ordinary (cache-allocating) stores
 
 class HostPool {
 public:
