@@ -7,7 +7,7 @@
  * evaluated ONCE per node and reused.  Because IEEE-754 arithmetic is deterministic, reusing the
  * value of an identical parenthesised sub-expression is bit-identical to recomputing it, so --
  * built with -ffp-contract=off, like the reference's own -O2 x86-64 build -- this file reproduces
- * the reference bit for bit (tests/test_oracle_vs_ref.py).  The association order of every product
+ * the reference bit for bit (tests/test_oracle.py).  The association order of every product
  * and sum below is the C left-to-right order of the cited reference line.
  *
  * All file:line citations are into /root/reference/. */

@@ -3,7 +3,7 @@
  * This is the CHECKER for libtolcuda, never the product: only tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs may load it.  Parity status: PINNED -- the
  * restatement is compared bit-for-bit with the unmodified reference compiled by oracle/Makefile
- * (oracle/_ref/libtolref.so) in tests/test_oracle_vs_ref.py and against the committed fixtures in
+ * (oracle/_ref/libtolref.so) in tests/test_oracle.py and against the committed fixtures in
  * tests/golden/ (generated from that same compiled reference by oracle/gen_golden.py).  The
  * reference ships no tests or golden vectors of its own.
  *
