@@ -172,6 +172,13 @@ int tolcuda_expand_compact_g(int formulation, int ts, long B, const double *Gc, 
  * TOLCUDA_COMPACT_G.  flags: 0 or TOLCUDA_NO_SYNC.  For results kept or gathered in compact form on the GPU. */
 int tolcuda_expand_compact_g_device(tolcuda_handle h, long B, const double *Gc, long ldGc, double *G, long ldG,
                                     int flags);
+/* Column-compressed (CSC) view of G for a device-side QP / factorisation (nothing of the kind in
+ * the reference, where SNOPT alone consumes G): colptr[n+1], rowidx[neG] (rows ascending within a column) and,
+ * optionally, perm[neG] = coordinate-order position of CSC entry p.  Host only.
+ * tolcuda_repack_csc_device gathers B rows of device memory from coordinate order into that order:
+ * Gcsc[b*ldC + p] = G[b*ldG + perm[p]], on the context's stream (flags: 0 or TOLCUDA_NO_SYNC). */
+int tolcuda_problem_pattern_csc(int formulation, int ts, int *colptr, int *rowidx, int *perm);
+int tolcuda_repack_csc_device(tolcuda_handle h, long B, const double *G, long ldG, double *Gcsc, long ldC, int flags);
 /* host threads the host-pointer batch path of this context expands compact rows with (0 = default:
  * environment TOLCUDA_HOST_THREADS, else the cores available to the process / LOCAL_WORLD_SIZE) */
 int tolcuda_set_host_threads(tolcuda_handle h, int threads);

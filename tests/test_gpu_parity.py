@@ -579,3 +579,25 @@ def test_shards_gathered_on_one_gpu_over_nccl(tmp_path):
     ev.close()
     assert np.array_equal(got["F"].view(np.int64), F.view(np.int64))
     assert np.array_equal(got["G"].view(np.int64), G.view(np.int64))
+
+
+@pytest.mark.parametrize("name", ["S10_tempest_ts200", "G7_skywalker_ts100", "S10_tempest_ts1"])
+def test_csc_repack_on_the_device(name):
+    """tolcuda_repack_csc_device: G rows gathered into column-compressed order on the GPU equal the same rows
+    permuted on the host with tolcuda_problem_pattern_csc's permutation (bit for bit), padding untouched"""
+    g = load_golden(name)
+    ev = T.Evaluator.from_golden(g)
+    B = 41
+    X = T.synth.batch(g["x"][0], 99, 0, B)
+    Xd = _dev(X)
+    Fd = torch.empty(B, ev.neF, dtype=torch.float64, device="cuda")
+    Gd = torch.empty(B, T.evaluator.padded_ld(ev.neG), dtype=torch.float64, device="cuda")
+    ev.eval_batch_device(Xd, Fd, Gd)
+    Gc = torch.full((B, ev.neG + 5), float("nan"), dtype=torch.float64, device="cuda")
+    ev.repack_csc_device(Gd, Gc)
+    _, _, pm = T.problem_pattern_csc(str(g["mission"]), int(g["ts"]))
+    want = Gd.cpu().numpy()[:, :ev.neG][:, pm]
+    got = Gc.cpu().numpy()
+    assert np.array_equal(np.ascontiguousarray(got[:, :ev.neG]).view(np.int64), np.ascontiguousarray(want).view(np.int64))
+    assert np.isnan(got[:, ev.neG:]).all()
+    ev.close()

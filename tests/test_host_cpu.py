@@ -248,3 +248,20 @@ int main(void) { return user_function == 0 || batch == 0 || sizeof(tolcuda_confi
                                "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
                                "-L", os.path.dirname(T.LIB_PATH), "-ltolcuda", "-Wl,-rpath," + os.path.dirname(T.LIB_PATH)])
         assert subprocess.run([str(exe)]).returncode == 0
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_csc_pattern_is_the_column_compressed_form_of_the_reference_pattern(name):
+    """tolcuda_problem_pattern_csc against scipy's COO -> CSC conversion of the REFERENCE's (iGfun, jGvar)"""
+    import scipy.sparse as sp
+    g = load_golden(name)
+    m, ts, n, neF, neG = str(g["mission"]), int(g["ts"]), int(g["n"]), int(g["neF"]), int(g["neG"])
+    cp, ri, pm = T.problem_pattern_csc(m, ts)
+    A = sp.coo_matrix((np.arange(1, neG + 1, dtype=float), (g["iGfun"], g["jGvar"])), shape=(neF, n)).tocsc()
+    A.sort_indices()
+    assert np.array_equal(A.indptr, cp) and np.array_equal(A.indices, ri) and np.array_equal(A.data, pm + 1.0)
+    # values: G in CSC order is the reference's G permuted
+    Gc = g["G"][:, pm]
+    B = sp.csc_matrix((Gc[0], ri, cp), shape=(neF, n))
+    C = sp.coo_matrix((g["G"][0], (g["iGfun"], g["jGvar"])), shape=(neF, n))
+    assert abs(B - C).max() == 0

@@ -77,7 +77,34 @@ expand_kernel(const int ts, const int R0, const int nbG, const double *__restric
     }
 }
 
+// coordinate order -> column-compressed order: out[b][p] = G[b][perm[p]].  Writes are coalesced; the reads of a
+// block stay within a few neighbouring window records (a column of node k gathers from the records of windows
+// k-1 and k), i.e. in L1/L2.
+__global__ void __launch_bounds__(256)
+repack_kernel(const int neG, const int *__restrict__ perm, const double *__restrict__ G, const long ldG,
+              double *__restrict__ out, const long ldo) {
+    const double *src = G + (size_t)blockIdx.y * ldG;
+    double *dst = out + (size_t)blockIdx.y * ldo;
+    const int p0 = blockIdx.x * 2048;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int p = p0 + threadIdx.x + 256 * i;
+        if (p < neG) dst[p] = __ldg(src + __ldg(perm + p));
+    }
+}
+
 }  // namespace
+
+cudaError_t repack_launch(int neG, const int *perm, long B, const double *G, long ldG, double *out, long ldo,
+                          cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    for (long b0 = 0; b0 < B; b0 += 65535) {  // gridDim.y limit
+        const long nb = B - b0 < 65535 ? B - b0 : 65535;
+        const dim3 grid((neG + 2047) / 2048, (unsigned)nb);
+        repack_kernel<<<grid, 256, 0, stream>>>(neG, perm, G + b0 * ldG, ldG, out + b0 * ldo, ldo);
+    }
+    return cudaGetLastError();
+}
 
 cudaError_t expand_launch(int form, int ts, int R0, int nbG, long B, const double *Gc, long ldGc, double *G,
                           long ldG, cudaStream_t stream) {

@@ -37,4 +37,8 @@ cudaError_t fg_launch(const FgLaunch &L);
 cudaError_t expand_launch(int form, int ts, int R0, int nbG, long B, const double *Gc, long ldGc, double *G,
                           long ldG, cudaStream_t stream);
 
+// enqueue out[b][p] = G[b][perm[p]] for B rows (coordinate order -> column-compressed order); device pointers
+cudaError_t repack_launch(int neG, const int *perm, long B, const double *G, long ldG, double *out, long ldo,
+                          cudaStream_t stream);
+
 #endif

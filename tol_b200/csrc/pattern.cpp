@@ -76,4 +76,25 @@ void pattern_build(int form, int ts, std::vector<int> &iG, std::vector<int> &jG)
     }
 }
 
+// Column-compressed view of the same pattern: colptr[n+1], rowidx[neG] and, for every CSC position p, the
+// position perm[p] of that entry in coordinate (row-major) order.  Entries of a column keep their row order
+// (a stable counting sort by column), which is what a CSC consumer expects.
+void pattern_csc(int form, int ts, std::vector<int> &colptr, std::vector<int> &rowidx, std::vector<int> &perm) {
+    int n, neF, neG;
+    pattern_dims(form, ts, &n, &neF, &neG, nullptr, nullptr);
+    std::vector<int> iG, jG;
+    pattern_build(form, ts, iG, jG);
+    colptr.assign(n + 1, 0);
+    for (int e = 0; e < neG; e++) colptr[jG[e] + 1]++;
+    for (int j = 0; j < n; j++) colptr[j + 1] += colptr[j];
+    rowidx.assign(neG, 0);
+    perm.assign(neG, 0);
+    std::vector<int> next(colptr.begin(), colptr.end() - 1);
+    for (int e = 0; e < neG; e++) {
+        const int p = next[jG[e]]++;
+        rowidx[p] = iG[e];
+        perm[p] = e;
+    }
+}
+
 }  // namespace tolcuda

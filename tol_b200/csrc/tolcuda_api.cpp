@@ -70,6 +70,7 @@ struct tolcuda_ctx {
     std::unique_ptr<HostPool> pool;
     long launches = 0;
     double *d_grid = nullptr;  // wind cube: gx | gy | gz | v
+    int *d_perm = nullptr;     // CSC position -> coordinate-order position, uploaded at first use
 };
 
 namespace {
@@ -348,6 +349,7 @@ int tolcuda_destroy(tolcuda_handle h) {
     if (h->h_one) cudaFreeHost(h->h_one);
     if (h->d_one) cudaFree(h->d_one);
     if (h->d_grid) cudaFree(h->d_grid);
+    if (h->d_perm) cudaFree(h->d_perm);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return 0;
@@ -622,6 +624,37 @@ int tolcuda_expand_compact_g_device(tolcuda_handle h, long B, const double *Gc, 
     CU(cudaSetDevice(h->cfg.device));
     cudaError_t e = expand_launch(c.form, c.ts, c.R0, c.nbG, B, Gc, ldGc, G, ldG, h->stream);
     if (e != cudaSuccess) return cuda_fail(e, "expand_launch");
+    h->launches += B > 0 ? (B + 65534) / 65535 : 0;
+    if (!(flags & TOLCUDA_NO_SYNC)) CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int tolcuda_problem_pattern_csc(int formulation, int ts, int *colptr, int *rowidx, int *perm) {
+    if ((formulation != TOLCUDA_G7 && formulation != TOLCUDA_S10) || ts < 1 || !colptr || !rowidx) return TOLCUDA_EINVAL;
+    std::vector<int> cp, ri, pm;
+    pattern_csc(formulation, ts, cp, ri, pm);
+    std::memcpy(colptr, cp.data(), sizeof(int) * cp.size());
+    std::memcpy(rowidx, ri.data(), sizeof(int) * ri.size());
+    if (perm) std::memcpy(perm, pm.data(), sizeof(int) * pm.size());
+    return 0;
+}
+
+int tolcuda_repack_csc_device(tolcuda_handle h, long B, const double *G, long ldG, double *Gcsc, long ldC, int flags) {
+    if (!h || B < 0) return TOLCUDA_EINVAL;
+    const FgConst &c = h->c;
+    if (B > 0 && (!G || !Gcsc || ldG < c.neG || ldC < c.neG)) {
+        set_error("tolcuda_repack_csc_device: null pointer or leading dimension shorter than the row");
+        return TOLCUDA_EINVAL;
+    }
+    CU(cudaSetDevice(h->cfg.device));
+    if (!h->d_perm) {
+        std::vector<int> cp, ri, pm;
+        pattern_csc(c.form, c.ts, cp, ri, pm);
+        CU(cudaMalloc(&h->d_perm, sizeof(int) * pm.size()));
+        CU(cudaMemcpy(h->d_perm, pm.data(), sizeof(int) * pm.size(), cudaMemcpyHostToDevice));
+    }
+    cudaError_t e = repack_launch(c.neG, h->d_perm, B, G, ldG, Gcsc, ldC, h->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "repack_launch");
     h->launches += B > 0 ? (B + 65534) / 65535 : 0;
     if (!(flags & TOLCUDA_NO_SYNC)) CU(cudaStreamSynchronize(h->stream));
     return 0;

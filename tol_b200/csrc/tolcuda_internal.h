@@ -21,6 +21,7 @@ void set_error(const std::string &msg);
 
 void pattern_dims(int form, int ts, int *n, int *neF, int *neG, int *R0, int *nbG);
 void pattern_build(int form, int ts, std::vector<int> &iG, std::vector<int> &jG);
+void pattern_csc(int form, int ts, std::vector<int> &colptr, std::vector<int> &rowidx, std::vector<int> &perm);
 
 void initial_guess(const tolcuda_config &cfg, double *x);
 void bounds(const tolcuda_config &cfg, double *xlow, double *xupp, double *Flow, double *Fupp);

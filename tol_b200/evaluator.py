@@ -35,6 +35,14 @@ def problem_pattern(mission, ts):
     return i, j
 
 
+def problem_pattern_csc(mission, ts):
+    """tolcuda_problem_pattern_csc: colptr[n+1], rowidx[neG], perm[neG] (CSC position -> coordinate-order position)"""
+    n, _, neG = problem_dims(mission, ts)
+    cp, ri, pm = np.empty(n + 1, np.int32), np.empty(neG, np.int32), np.empty(neG, np.int32)
+    _l.check(_l.load().tolcuda_problem_pattern_csc(_FORM[mission], int(ts), _ip(cp), _ip(ri), _ip(pm)))
+    return cp, ri, pm
+
+
 def read_params(path, cap=64):
     v = np.zeros(cap)
     cnt = C.c_int()
@@ -227,6 +235,11 @@ class Evaluator:
         coordinate order (torch CUDA tensor [B, >= neG]) on the context's stream"""
         _l.check(self.L.tolcuda_expand_compact_g_device(self.h, Gc.shape[0], Gc.data_ptr(), Gc.stride(0), G.data_ptr(),
                                                         G.stride(0), 0 if sync else NO_SYNC))
+
+    def repack_csc_device(self, G, Gcsc, sync=True):
+        """tolcuda_repack_csc_device: rows in coordinate order -> rows in CSC order (torch CUDA tensors)"""
+        _l.check(self.L.tolcuda_repack_csc_device(self.h, G.shape[0], G.data_ptr(), G.stride(0), Gcsc.data_ptr(),
+                                                  Gcsc.stride(0), 0 if sync else NO_SYNC))
 
     def summary_host(self, X, needF=False, needG=False):
         """tolcuda_eval_batch_summary with host arrays: [B, 4] = objective, max|defect|, max boundary

@@ -54,6 +54,8 @@ def load():
     L.tolcuda_compact_len.restype = C.c_long
     L.tolcuda_expand_compact_g.argtypes = [C.c_int, C.c_int, C.c_long, vp, C.c_long, vp, C.c_long, C.c_int]
     L.tolcuda_set_host_threads.argtypes = [vp, C.c_int]
+    L.tolcuda_problem_pattern_csc.argtypes = [C.c_int, C.c_int, ip, ip, ip]
+    L.tolcuda_repack_csc_device.argtypes = [vp, C.c_long, vp, C.c_long, vp, C.c_long, C.c_int]
     L.tolcuda_expand_compact_g_device.argtypes = [vp, C.c_long, vp, C.c_long, vp, C.c_long, C.c_int]
     L.tolcuda_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.tolcuda_host_free.argtypes = [vp]

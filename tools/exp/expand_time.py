@@ -10,7 +10,9 @@ Gc=torch.empty(B,padded_ld(ev.compact_len),dtype=torch.float64,device="cuda")
 G=torch.empty(B,padded_ld(ev.neG),dtype=torch.float64,device="cuda")
 st=torch.cuda.Stream(); torch.cuda.set_stream(st); ev.set_stream(st.cuda_stream)
 ev.eval_batch_device(X,F,Gc,compact_rows=True)
-for fn,name,by in ((lambda: ev.expand_compact_device(Gc,G,sync=False),"device expansion",8*B*(ev.compact_len+ev.neG)),):
+G2=torch.empty(B,padded_ld(ev.neG),dtype=torch.float64,device="cuda")
+ev.repack_csc_device(G,G2)
+for fn,name,by in ((lambda: ev.expand_compact_device(Gc,G,sync=False),"device expansion",8*B*(ev.compact_len+ev.neG)),(lambda: ev.repack_csc_device(G,G2,sync=False),"CSC repack",8*B*2*ev.neG)):
     for _ in range(3): fn()
     e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
     e0.record(st)
