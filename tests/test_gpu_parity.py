@@ -157,7 +157,7 @@ def test_compact_rows_path_equals_full_rows(name, kernel, monkeypatch):
 @pytest.mark.parametrize("kernel", [1, 2])
 def test_section_8d_batches_against_oracle(name, seed0, kernel, monkeypatch, oracle_built):
     """configs 3 and 4 of BASELINE.json on a 64-trajectory subset, through both kernels (CTA per
-    trajectory / persistent warps); the lane-copy fallback of the TMA bulk
+    run of trajectories / CTA per trajectory with a tile loop); the lane-copy fallback of the TMA bulk
     stores is exercised by the odd-leading-dimension cases of test_batch_device_pointers"""
     monkeypatch.setenv("TOLCUDA_KERNEL", str(kernel))
     g = load_golden(name)
@@ -294,7 +294,7 @@ def test_tolbatch_driver_end_to_end(tmp_path):
 
 @pytest.mark.parametrize("mission,ts", [("S10", 257), ("G7", 300), ("S10", 1100), ("G7", 2049)])
 def test_long_trajectories(mission, ts, oracle_built):
-    """ts > 256 is routed to the persistent-warp kernel (a warp walks the tiles of a trajectory in turn);
+    """ts > 256 is routed to kernel L (one CTA per trajectory, each warp walking several tiles);
     inputs: the restated InitialCond (bit-identical to the reference's) perturbed per SURVEY.md 8d;
     checker: the oracle port"""
     g = load_golden("S10_tempest_ts100" if mission == "S10" else "G7_skywalker_ts100")

@@ -76,7 +76,7 @@ constexpr int TILE_LEN = NBUF * BUF_LEN;
 constexpr int SX_LEN = 368;            // a warp's x slice: slot for x[11*k0] + 33 nodes = 364 doubles (tile stays 128-byte aligned)
 static_assert(NPP % UNIT == 0 && 32 % NPP == 0 && PADW % 2 == 0 && NBUF * NPP <= 32, "record buffer layout");
 constexpr int WARP_SMEM = SX_LEN + TILE_LEN;        // kernel A
-constexpr int WARP_SMEM_B = 2 * SX_LEN + TILE_LEN;  // kernel B: double-buffered x slice
+constexpr int WARP_SMEM_B = 2 * SX_LEN + TILE_LEN;  // kernel L (and kernel A with runs): two x-slice buffers
 constexpr int F_LD = 10;               // smem stride of a window's 8 defects (== 2 mod 4)
 constexpr int NVAR = TOLCUDA_NVAR;     // x-dependent entries of a record (plus two -dt entries)
 // kernel flavours: plain F/G; F/G + per-trajectory summary; F + COMPACT G (objective-row block, then the
@@ -827,79 +827,95 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int B, int per_arg, const doubl
     cp_async_wait<0>();
 }
 
-// ---- kernel B: persistent warps, one trajectory per warp at a time ------------------------------------------
+// ---- kernel L: one CTA per trajectory of any length -------------------------------------------------------------
 //
-// Every warp walks trajectories b = warp_id, warp_id + total_warps, ... and, within a trajectory, its
-// tiles in order, so cost sums stay in registers and no warp ever waits for another.  While a tile is
-// evaluated, the x slice of the next tile (or of the next trajectory's first tile) is already in flight
-// (cp.async) into the other slice buffer.  Serves trajectories longer than 256 windows (any ts), and every
-// trajectory with TOLCUDA_KERNEL=2; 0.82 of the roofline on S10 ts=200 against kernel A's 0.98.
-template <int FORM, int WIND, int WARPS, int MINB, int MODE>
-__global__ void __launch_bounds__(WARPS * 32, MINB)
-fg_warp_kernel(const __grid_constant__ FgConst c, int B, const double *__restrict__ x, long ldx,
+// Up to 8 warps (the host picks the count that balances the tiles); warp w walks tiles w, w+W, w+2W, ... of the trajectory, keeping its share of the cost
+// sums in registers, while the slice of its next tile is already in flight into the other slice buffer; the sums
+// cross warps once per trajectory as in kernel A.  Serves trajectories longer than 256 windows (and any
+// trajectory with TOLCUDA_KERNEL=2).  All warps of a CTA write the same G row, as in kernel A: the earlier
+// persistent-warp kernel (one whole trajectory per warp, 16 x 148 rows being written at a time) reached 0.82 of
+// the roofline on S10 ts=200 where kernel A reaches 0.98.
+constexpr int LWARPS = 8;
+template <int FORM, int WIND, int MODE>
+__global__ void __launch_bounds__(LWARPS * 32, 2)
+fg_long_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, long ldx,
                double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG,
                double *__restrict__ S, long ldS) {
     constexpr bool SUMM = (MODE == MODE_SUMMARY);
     extern __shared__ __align__(16) double smem[];
+    __shared__ double red[SUMM ? 4 : 2][32];
+    __shared__ int arrivals;
     const int ts = c.ts;
     const int nt = (ts + 31) >> 5;
     const int tid = thread_index();
-    const int lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform, see kernel A
+    const int lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), nwarps = blockDim.x >> 5;
     double *wsm = smem + (size_t)warp * WARP_SMEM_B;
     double *tile = wsm + 2 * SX_LEN;
     const uint32_t wsm_s = smem_addr(wsm), tile_s = wsm_s + 8 * 2 * SX_LEN;
-    const int total = gridDim.x * WARPS;
-    int b = blockIdx.x * WARPS + warp, t = 0, buf = 0;
-    if (b >= B) return;
-
-    slice_prefetch(wsm_s, x + (size_t)b * ldx, 1 + PX * (min(32, ts) + 1), lane);
+    const size_t b = blockIdx.x;
+    const double *xb = x + b * ldx;
+    double *Fb = F + b * ldF, *Gb = G + b * ldG;
+    slice_prefetch(wsm_s, xb + (size_t)PX * 32 * warp, 1 + PX * (min(32, ts - 32 * warp) + 1), lane);
     cp_async_commit();
+    const double dt = __ldg(xb);
+    double n0 = 0.0, ne = 0.0;
+    if (lane < PX) {
+        n0 = __ldg(xb + 1 + lane);
+        ne = __ldg(xb + (size_t)PX * ts + 1 + lane);
+    }
     if (needG) tile_init(tile, lane);
-    double dt = 0.0, n0 = 0.0, accT = 0.0, accp = 0.0, accm = 0.0, accq = 0.0;
+    if (tid == 0) arrivals = 0;
+    __syncthreads();
+    double accT = 0.0, accp = 0.0, accm = 0.0, accq = 0.0;
+    int slot = 0;
 #pragma unroll 1
-    while (b < B) {
-        int nb = b, ntile = t + 1;
-        if (ntile == nt) {
-            nb = b + total;
-            ntile = 0;
-        }
-        double *sx = wsm + buf * SX_LEN;  // current slice; the other one receives the prefetch
-        if (nb < B) {
-            const int nk2 = min(32, ts - 32 * ntile);
-            slice_prefetch(wsm_s + 8 * (buf ^ 1) * SX_LEN, x + (size_t)nb * ldx + (size_t)PX * 32 * ntile,
-                           1 + PX * (nk2 + 1), lane);
-        }
+    for (int j = warp; j < nt; j += nwarps) {
+        const int jn = j + nwarps;
+        if (jn < nt)
+            slice_prefetch(wsm_s + 8 * (slot ^ 1) * SX_LEN, xb + (size_t)PX * 32 * jn, 1 + PX * (min(32, ts - 32 * jn) + 1), lane);
         cp_async_commit();
         cp_async_wait<1>();
         __syncwarp();
-
-        const int k0 = 32 * t, nk = min(32, ts - k0);
-        if (t == 0) {
-            dt = sx[0];
-            n0 = lane < PX ? sx[1 + lane] : 0.0;
-        }
-        const double ne = (t == nt - 1 && lane < PX) ? sx[1 + PX * nk + lane] : 0.0;
-        double *Fb = F + (size_t)b * ldF, *Gb = G + (size_t)b * ldG;
         TileSums tsum;
-        tile_eval<FORM, WIND, MODE>(c, sx, tile, tile_s, dt, k0, nk, lane, Fb, Gb, needF, needG, tsum);
+        tile_eval<FORM, WIND, MODE>(c, wsm + slot * SX_LEN, tile, tile_s, dt, 32 * j, min(32, ts - 32 * j), lane, Fb, Gb,
+                                    needF, needG, tsum);
+        __syncwarp();
         accT += tsum.sumT;
         accp += tsum.sump;
         accm = fmax(accm, tsum.dmax);
         accq += tsum.dssq;
-        if (t == nt - 1) {
-            const double tT = warp_sum(accT);
-            const double tp = FORM == TOLCUDA_FORM_S10 ? warp_sum(accp) : 0.0;
-            const double dmax = SUMM ? warp_max(accm) : 0.0, dssq = SUMM ? warp_sum(accq) : 0.0;
-            traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG, dmax, dssq,
-                                SUMM ? S + (size_t)b * ldS : nullptr, MODE == MODE_COMPACT ? NVAR : REC);
-            accT = accp = accm = accq = 0.0;
-        }
-        __syncwarp();
-        b = nb;
-        t = ntile;
-        buf ^= 1;
+        slot ^= 1;
     }
     cp_async_wait<0>();
+    const double sumT = warp_sum(accT);
+    const double sump = FORM == TOLCUDA_FORM_S10 ? warp_sum(accp) : 0.0;
+    const double wdmax = SUMM ? warp_max(accm) : 0.0, wdssq = SUMM ? warp_sum(accq) : 0.0;
+    int last = 0;
+    if (lane == 0) {
+        red[0][warp] = sumT;
+        red[1][warp] = sump;
+        if (SUMM) {
+            red[SUMM ? 2 : 0][warp] = wdmax;
+            red[SUMM ? 3 : 0][warp] = wdssq;
+        }
+        __threadfence_block();
+        last = (atomicAdd(&arrivals, 1) == nwarps - 1);
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence_block();
+    const volatile double *vred = &red[0][0];
+    double tT = 0.0, tp = 0.0, dmax = 0.0, dssq = 0.0;
+    for (int w = 0; w < nwarps; w++) {  // fixed order: deterministic
+        tT += vred[w];
+        tp += vred[32 + w];
+        if (SUMM) {
+            dmax = fmax(dmax, vred[64 + w]);
+            dssq += vred[96 + w];
+        }
+    }
+    traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG, dmax, dssq, SUMM ? S + b * ldS : nullptr,
+                        MODE == MODE_COMPACT ? NVAR : REC);
 }
 
 template <int FORM, int WIND, int MAXT, int MINB, int MODE, bool LOOP>
@@ -929,32 +945,31 @@ cudaError_t launch_cta(const FgLaunch &L) {
                     : launch_cta_as<FORM, WIND, MAXT, MINB, MODE, true>(L, per);
 }
 
-template <int FORM, int WIND, int WARPS, int MINB, int MODE>
-cudaError_t launch_warp(const FgLaunch &L) {
-    auto kern = fg_warp_kernel<FORM, WIND, WARPS, MINB, MODE>;
-    const size_t smem = sizeof(double) * (size_t)WARPS * WARP_SMEM_B;
-    static std::atomic<size_t> configured[MAX_DEVICES];  // per device, see launch_cta
+template <int FORM, int WIND, int MODE>
+cudaError_t launch_long(const FgLaunch &L) {
+    auto kern = fg_long_kernel<FORM, WIND, MODE>;
+    // as many warps (<= 8) as give every warp the same number of tiles, give or take one: 10 tiles -> 5 warps x 2
+    const int nt = (L.c->ts + 31) / 32;
+    const int rounds = (nt + LWARPS - 1) / LWARPS;
+    const int nthr = 32 * ((nt + rounds - 1) / rounds);
+    const size_t smem = sizeof(double) * (size_t)(nthr / 32) * WARP_SMEM_B;
+    static std::atomic<size_t> configured[MAX_DEVICES];  // per device, see launch_cta_as
     std::atomic<size_t> &done = configured[L.device & (MAX_DEVICES - 1)];
     if (smem > done.load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         done.store(smem, std::memory_order_release);
     }
-    const int resident = L.sm_count * MINB;  // persistent: one wave of CTAs
-    const int want = (L.B + WARPS - 1) / WARPS;
-    const int grid = want < resident ? want : resident;
-    kern<<<grid, WARPS * 32, smem, L.stream>>>(*L.c, L.B, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG,
-                                               L.S, L.ldS);
+    kern<<<L.B, nthr, smem, L.stream>>>(*L.c, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG, L.S, L.ldS);
     return cudaGetLastError();
 }
 
 template <int FORM, int WIND, int MODE>
 cudaError_t launch_sel(const FgLaunch &L) {
-    // Kernel A (one CTA per run of trajectories) needs the whole trajectory in one CTA at a register budget that
-    // does not spill: ts <= 256.  Longer trajectories, and L.kernel == 2, take kernel B, whose warps walk
-    // the tiles of a trajectory one after the other (any ts).
+    // Kernel A needs the whole trajectory in one CTA with one tile per warp: ts <= 256.  Longer trajectories,
+    // and L.kernel == 2, take kernel L, whose warps walk several tiles each (any ts).
     const int ts = L.c->ts;
-    if (L.kernel == 2 || ts > 256) return launch_warp<FORM, WIND, 4, 4, MODE>(L);  // 128 registers, 16 warps / SM
+    if (L.kernel == 2 || ts > 256) return launch_long<FORM, WIND, MODE>(L);
     if (ts <= 128) return launch_cta<FORM, WIND, 128, 4, MODE>(L);                 // 128 registers, 16 warps / SM
     return launch_cta<FORM, WIND, 256, 2, MODE>(L);                          // 128 registers, 14-16 warps / SM
 }

@@ -22,7 +22,7 @@ struct FgLaunch {
     double *S;  // optional per-trajectory summary [B][ldS >= 4]: objective, max|defect|, max|boundary|, sum defect^2
     long ldS;
     int compact;  // G/ldG address the compact layout [R0 | 31 per window | boundary block] (host-pointer path)
-    int kernel;    // 0/1 = kernel A (CTA per run of trajectories), 2 = kernel B (persistent warps)
+    int kernel;    // 0/1 = kernel A (CTA per run of trajectories), 2 = kernel L (CTA per trajectory, tile loop; any ts)
     int per;       // kernel A: trajectories per CTA (1..4)
     int per_auto;  // 1: small batches (B < 48 x SMs) use 1 regardless of `per`
     int sm_count;  // SMs of the device

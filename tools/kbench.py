@@ -23,6 +23,7 @@ ap.add_argument("--kernel", type=int, default=0)
 ap.add_argument("--goff", type=int, default=0, help="shift the G buffer by this many doubles (alignment experiments)")
 ap.add_argument("--need", default="FG")
 ap.add_argument("--distinct", type=int, default=512, help="distinct synthetic trajectories (tiled)")
+ap.add_argument("--ts", type=int, default=0, help="override the number of windows (x0 = the restated InitialCond for that ts)")
 args = ap.parse_args()
 if args.kernel:
     os.environ["TOLCUDA_KERNEL"] = str(args.kernel)
@@ -30,13 +31,21 @@ import tol_b200 as T  # noqa: E402
 from tol_b200.evaluator import padded_ld  # noqa: E402
 
 g = np.load(os.path.join(ROOT, "tests", "golden", args.workload + ".npz"))
-ev = T.Evaluator.from_golden(g)
-B, n, neF, neG, ts = args.batch, ev.n, ev.neF, ev.neG, int(g["ts"])
+if args.ts:
+    lm = g["lm"]
+    cfg = T.make_config(str(g["mission"]), args.ts, g["ac"], g["gn"], g["goal_ned"],
+                        limits=[lm[0], lm[1], lm[5], lm[2], lm[6], lm[3], lm[7], lm[4]])
+    x0 = T.initial_guess(cfg)
+    ev = T.Evaluator(str(g["mission"]), args.ts, g["ac"], g["gn"], g["goal_ned"])
+else:
+    x0 = g["x"][0]
+    ev = T.Evaluator.from_golden(g)
+B, n, neF, neG, ts = args.batch, ev.n, ev.neF, ev.neG, args.ts or int(g["ts"])
 ldx, ldF, ldG = padded_ld(n), padded_ld(neF), padded_ld(neG)
 seed0 = T.synth.SEED_S10 if str(g["mission"]) == "S10" else T.synth.SEED_G7
 U = min(B, args.distinct)
 Xu = torch.zeros(U, ldx, dtype=torch.float64)
-T.synth.batch(g["x"][0], seed0, 0, U, out=Xu.numpy())
+T.synth.batch(x0, seed0, 0, U, out=Xu.numpy())
 Xd = Xu.cuda()[torch.arange(B, device="cuda") % U].contiguous()
 Fd = torch.empty(B, ldF, dtype=torch.float64, device="cuda")
 Gd = torch.empty(B * ldG + 64, dtype=torch.float64, device="cuda")[args.goff:args.goff + B * ldG].view(B, ldG)
