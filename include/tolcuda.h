@@ -5,7 +5,13 @@
  * cudaError_t value on a CUDA failure, or a negative TOLCUDA_E* code; none throws across the ABI.
  * tolcuda_last_error() returns a human-readable message for the calling thread's last failure.
  *
- * There is NO CPU fallback: every evaluation runs the sm_100a kernels in fg_kernels.cu. */
+ * There is NO CPU fallback: every evaluation runs the sm_100a kernels in fg_kernels.cu.
+ *
+ * Threading: a handle owns its streams and staging buffers and is NOT re-entrant -- one call at a time per
+ * handle (the reference callback is single-threaded too: process-global `prob`, src/tol.cpp:3).  Different
+ * handles, e.g. one per device, may be used from different threads concurrently (tolbatch does).  The
+ * context-free queries (tolcuda_problem_*, tolcuda_compact_len, tolcuda_expand_compact_g, tolcuda_write_results_*,
+ * tolcuda_read_params) are thread-safe. */
 #ifndef TOLCUDA_H_
 #define TOLCUDA_H_
 
