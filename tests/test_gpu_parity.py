@@ -601,3 +601,29 @@ def test_csc_repack_on_the_device(name):
     assert np.array_equal(np.ascontiguousarray(got[:, :ev.neG]).view(np.int64), np.ascontiguousarray(want).view(np.int64))
     assert np.isnan(got[:, ev.neG:]).all()
     ev.close()
+
+
+def test_more_rows_than_one_grid_dimension():
+    """B > 65,535 (the y-dimension limit of a grid) through the batch kernel, the device expansion and the CSC
+    repack, on a small problem: rows far apart in the batch must equal their single-trajectory evaluation"""
+    g = load_golden("S10_skywalker_ts7_gains")
+    ev = T.Evaluator.from_golden(g)
+    B, U = 70001, 11
+    Xu = T.synth.batch(g["x"][0], 8, 0, U)
+    Xd = _dev(Xu)[torch.arange(B, device="cuda") % U].contiguous()
+    Fd = torch.empty(B, ev.neF, dtype=torch.float64, device="cuda")
+    Gd = torch.empty(B, ev.neG, dtype=torch.float64, device="cuda")
+    Gc = torch.empty(B, ev.compact_len, dtype=torch.float64, device="cuda")
+    ev.eval_batch_device(Xd, Fd, Gd)
+    ev.eval_batch_device(Xd, Fd, Gc, compact_rows=True)
+    Gx = torch.empty_like(Gd)
+    ev.expand_compact_device(Gc, Gx)
+    assert torch.equal(Gx, Gd)
+    Gs = torch.empty_like(Gd)
+    ev.repack_csc_device(Gd, Gs)
+    _, _, pm = T.problem_pattern_csc("S10", 7)
+    assert torch.equal(Gs, Gd[:, torch.from_numpy(pm.astype(np.int64)).cuda()])
+    for b in (0, 65534, 65535, 65536, 70000):
+        F1, G1 = ev.eval(Xu[b % U])
+        assert np.array_equal(Fd[b].cpu().numpy(), F1) and np.array_equal(Gd[b].cpu().numpy(), G1)
+    ev.close()
