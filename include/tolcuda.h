@@ -206,6 +206,28 @@ int tolcuda_host_alloc(size_t bytes, void **ptr);
 int tolcuda_host_free(void *ptr);
 int tolcuda_device_count(int *count);
 
+/* Result buffers that OTHER GPUs of the box write directly ("optional NVLink gather of results
+ * to one GPU"; nothing of the kind in the reference).  The F/G kernels store through ordinary global
+ * addresses (F: coalesced stores, G: TMA bulk copies), so F/G of tolcuda_eval_batch may point into the memory of
+ * a peer GPU: the shard then lands in the gathering GPU's rows over NVLink while it is being computed -- one
+ * kernel, no staging copy and no collective afterwards.
+ *   one process per GPU   the gathering process allocates with tolcuda_device_alloc, exports the allocation with
+ *                         tolcuda_ipc_export (a CUDA IPC handle: TOLCUDA_IPC_HANDLE_BYTES opaque bytes to send over
+ *                         any channel); every other process maps it with tolcuda_ipc_open on ITS device (peer access
+ *                         is enabled by the mapping) and passes `mapped + offset of its rows` as F/G with
+ *                         TOLCUDA_DEVICE_PTRS; after its call has returned (synchronised) its rows are visible
+ *                         to the owner; tolcuda_ipc_close unmaps.
+ *   one process, several devices (tolbatch)   tolcuda_enable_peer(device, peer) once per ordered pair, then any
+ *                         cudaMalloc / tolcuda_device_alloc pointer of `peer` is valid in kernels of `device`.
+ * x always stays on the evaluating GPU. */
+#define TOLCUDA_IPC_HANDLE_BYTES 64
+int tolcuda_device_alloc(int device, size_t bytes, void **ptr);
+int tolcuda_device_free(int device, void *ptr);
+int tolcuda_ipc_export(int device, const void *ptr, unsigned char handle[TOLCUDA_IPC_HANDLE_BYTES]);
+int tolcuda_ipc_open(int device, const unsigned char handle[TOLCUDA_IPC_HANDLE_BYTES], void **ptr);
+int tolcuda_ipc_close(int device, void *ptr);
+int tolcuda_enable_peer(int device, int peer);
+
 /* smallest multiple of 16 doubles (128 bytes) that holds `len` doubles */
 long tolcuda_padded_ld(long len);
 

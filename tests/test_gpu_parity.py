@@ -627,3 +627,81 @@ def test_more_rows_than_one_grid_dimension():
         F1, G1 = ev.eval(Xu[b % U])
         assert np.array_equal(Fd[b].cpu().numpy(), F1) and np.array_equal(Gd[b].cpu().numpy(), G1)
     ev.close()
+
+
+def test_peer_buffer_rows_on_one_gpu():
+    """tolcuda_device_alloc / tolcuda_ipc_export + tolcuda_eval_batch on raw addresses (the world-size-1 leg of
+    the fused evaluate + gather): the rows written into the exported buffer are bit for bit those of an ordinary
+    device-pointer call, and the padding between rows is untouched"""
+    import tol_b200.dist as D
+    g = load_golden("S10_tempest_ts100")
+    ev = T.Evaluator.from_golden(g)
+    B = 29
+    X = _dev(T.synth.batch(g["x"][0], 4242, 0, B))
+    ldF, ldG = T.evaluator.padded_ld(ev.neF), T.evaluator.padded_ld(ev.neG)
+    buf = T.PeerBuffer.alloc(0, D.peer_buffer_bytes(ev, B, staged=False))
+    assert len(buf.handle) == T.evaluator.IPC_HANDLE_BYTES and any(buf.handle)
+    buf.tensor(0, 1, B * (ldF + ldG)).fill_(float("nan"))
+    F, G, kept = D.eval_and_gather_peer(ev, X, B, out=buf)
+    assert kept is buf and F.shape == (B, ldF) and G.shape == (B, ldG)
+    Fd = torch.empty(B, ev.neF, dtype=torch.float64, device="cuda")
+    Gd = torch.empty(B, ev.neG, dtype=torch.float64, device="cuda")
+    ev.eval_batch_device(X, Fd, Gd)
+    assert torch.equal(F[:, :ev.neF], Fd) and torch.equal(G[:, :ev.neG], Gd)
+    assert torch.isnan(F[:, ev.neF:]).all() and torch.isnan(G[:, ev.neG:]).all()
+    del F, G
+    ev.close()
+    buf.close()
+
+
+def _peer_gather_worker(rank, world, port, name, B, compact, out_path):
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    import tol_b200.dist as D
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    g = load_golden(name)
+    ev = T.Evaluator.from_golden(g, device=rank)
+    b0, b1 = D.my_shard(B)
+    X = torch.from_numpy(T.synth.batch(g["x"][0], 2718, b0, b1)).cuda()
+    dst = world - 1  # not rank 0: the owner is any rank
+    for _ in range(2):  # a second round maps the owner's (new) buffer again
+        F, G, buf = D.eval_and_gather_peer(ev, X, B, dst=dst, compact=compact)
+    if rank == dst:
+        np.savez(out_path, F=F[:, :ev.neF].cpu().numpy(), G=G[:, :ev.neG].cpu().numpy())
+    dist.barrier()
+    del F, G, buf
+    ev.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,B", [("S10_tempest_ts100", 37), ("G7_skywalker_ts100", 5), ("S10_tempest_ts200", 301)])
+@pytest.mark.parametrize("compact", [True, False])
+def test_shards_written_into_one_gpu_over_nvlink(name, B, compact, tmp_path):
+    """2+ GPUs, fused evaluate + gather: every rank's F/G kernel stores its shard's rows directly into the
+    gathering GPU's buffer (CUDA IPC mapping, NVLink peer stores: coalesced F stores and the G TMA bulk copies);
+    as compact rows expanded by the owner, or as full rows at their final place; the gathered rows must be
+    bit-identical to one GPU evaluating the whole batch"""
+    import socket
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "gathered.npz")
+    mp.spawn(_peer_gather_worker, args=(2, port, name, B, compact, out), nprocs=2, join=True)
+    got = np.load(out)
+    g = load_golden(name)
+    ev = T.Evaluator.from_golden(g)
+    F, G = ev.eval_batch_host(T.synth.batch(g["x"][0], 2718, 0, B), full_copy=True)
+    ev.close()
+    assert np.array_equal(got["F"].view(np.int64), F.view(np.int64))
+    assert np.array_equal(got["G"].view(np.int64), G.view(np.int64))

@@ -169,6 +169,69 @@ int tolcuda_device_count(int *count) {
     return 0;
 }
 
+// ---- result buffers written by peer GPUs over NVLink (include/tolcuda.h) ----
+
+int tolcuda_device_alloc(int device, size_t bytes, void **ptr) {
+    if (!ptr) return TOLCUDA_EINVAL;
+    *ptr = nullptr;
+    CU(cudaSetDevice(device));
+    CU(cudaMalloc(ptr, bytes));
+    return 0;
+}
+
+int tolcuda_device_free(int device, void *ptr) {
+    if (!ptr) return 0;
+    CU(cudaSetDevice(device));
+    CU(cudaFree(ptr));
+    return 0;
+}
+
+static_assert(sizeof(cudaIpcMemHandle_t) == TOLCUDA_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+
+int tolcuda_ipc_export(int device, const void *ptr, unsigned char *handle) {
+    if (!ptr || !handle) return TOLCUDA_EINVAL;
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t hd;
+    CU(cudaIpcGetMemHandle(&hd, const_cast<void *>(ptr)));
+    std::memcpy(handle, &hd, sizeof hd);
+    return 0;
+}
+
+int tolcuda_ipc_open(int device, const unsigned char *handle, void **ptr) {
+    if (!handle || !ptr) return TOLCUDA_EINVAL;
+    *ptr = nullptr;
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, handle, sizeof hd);
+    CU(cudaIpcOpenMemHandle(ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int tolcuda_ipc_close(int device, void *ptr) {
+    if (!ptr) return 0;
+    CU(cudaSetDevice(device));
+    CU(cudaIpcCloseMemHandle(ptr));
+    return 0;
+}
+
+int tolcuda_enable_peer(int device, int peer) {
+    if (device == peer) return 0;
+    int can = 0;
+    CU(cudaDeviceCanAccessPeer(&can, device, peer));
+    if (!can) {
+        set_error("tolcuda_enable_peer: no peer access between the two devices");
+        return TOLCUDA_EUNSUPPORTED;
+    }
+    CU(cudaSetDevice(device));
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return 0;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+    return 0;
+}
+
 int tolcuda_read_params(const char *path, double *values, int cap, int *count) {
     if (!path || !count) return TOLCUDA_EINVAL;
     std::vector<double> v;

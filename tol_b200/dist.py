@@ -1,7 +1,10 @@
 """One process per GPU, trajectories sharded by index, no collective on the data path (SURVEY.md
 section 8e).  torch.distributed is used for the three things around the path: agreeing on the shard
 ranges, the max-over-ranks of the timings, and the optional host-side gather of per-trajectory rows to
-rank 0 (the `north_star`'s "host-side gather of per-trajectory F/G")."""
+rank 0 (the `north_star`'s "host-side gather of per-trajectory F/G").  Two device-side gathers exist beside it
+(SURVEY.md section 8f-4): compact rows through one NCCL gather (eval_and_gather_device) and the fused form, in
+which every rank's F/G kernel writes its rows straight into the gathering GPU's memory over NVLink
+(eval_and_gather_peer)."""
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -86,3 +89,72 @@ def eval_and_gather_device(ev, X, B, dst=0):
             ev.expand_compact_device(Gp[q][:b1 - b0], G[b0:b1], sync=False)
     ev.synchronize()
     return F, G
+
+
+def eval_and_gather_peer(ev, X, B, dst=0, out=None, compact=True):
+    """Fused evaluate + gather: rank `dst` owns one buffer holding all B rows of F and
+    G; every other rank maps it over CUDA IPC (NVLink peer access) and its F/G kernel stores its shard's rows
+    directly into it -- F with coalesced stores, G with the kernel's TMA bulk copies -- so the transfer happens
+    record by record while the shard is being computed: no send buffer, no copy or collective afterwards.
+    torch.distributed only carries the 64-byte handle and the closing barrier.
+      compact=True   the peers' G crosses NVLink as COMPACT rows (a third of the bytes: NVLink, at 0.9 TB/s per
+                     direction, is the slower side) into a staging region of the same buffer, and `dst` expands
+                     them into rows in coordinate order at HBM speed (expand_kernel.cu)
+      compact=False  the peers write full rows at their final place; nothing runs on `dst` afterwards
+    Returns (F [B, ldF], G [B, ldG], buffer) as CUDA tensors on rank `dst` (rows by trajectory index, padded
+    leading dimensions), (None, None, None) elsewhere.  `out`: what open_peer_buffer returned on this rank, to
+    reuse the allocation and its mappings over many calls (mapping a handle costs far more than a launch)."""
+    from .evaluator import padded_ld
+    r, w = world()
+    b0, b1 = shard_range(B, r, w)
+    ldF, ldG, ldC = padded_ld(ev.neF), padded_ld(ev.neG), padded_ld(ev.compact_len)
+    staged = compact and w > 1
+    nbytes = peer_buffer_bytes(ev, B, staged)
+    buf = out if out is not None else open_peer_buffer(ev, B, dst, staged)
+    assert buf.nbytes >= nbytes
+    if b1 > b0:
+        assert X.shape[0] == b1 - b0
+        Fp = buf.ptr + 8 * b0 * ldF
+        if staged and r != dst:
+            ev.eval_batch_ptrs(b1 - b0, X.data_ptr(), X.stride(0), Fp, ldF,
+                               buf.ptr + 8 * (B * (ldF + ldG) + b0 * ldC), ldC, compact_rows=True)
+        else:
+            ev.eval_batch_ptrs(b1 - b0, X.data_ptr(), X.stride(0), Fp, ldF, buf.ptr + 8 * (B * ldF + b0 * ldG), ldG)
+        # (both return after this rank's stream has drained)
+    if w > 1:
+        dist.barrier()  # every shard has landed in the owner's memory
+        if r != dst:
+            if out is None:
+                buf.close()
+            return None, None, None
+    F, G = buf.tensor(0, B, ldF), buf.tensor(B * ldF, B, ldG)
+    if staged:
+        Gc = buf.tensor(B * (ldF + ldG), B, ldC)
+        for q in range(w):
+            q0, q1 = shard_range(B, q, w)
+            if q != dst and q1 > q0:
+                ev.expand_compact_device(Gc[q0:q1], G[q0:q1], sync=False)
+        ev.synchronize()
+    return F, G, buf
+
+
+def open_peer_buffer(ev, B, dst=0, staged=True):
+    """collective: rank `dst` allocates the gather buffer (peer_buffer_bytes) and exports it, every other rank
+    maps it on its own device; returns this rank's PeerBuffer (close() it when done)"""
+    from .evaluator import PeerBuffer
+    r, w = world()
+    nbytes = peer_buffer_bytes(ev, B, staged and w > 1)
+    buf = PeerBuffer.alloc(ev.device, nbytes) if r == dst else None
+    if w > 1:
+        box = [buf.handle if r == dst else None]
+        dist.broadcast_object_list(box, src=dst)
+        if r != dst:
+            buf = PeerBuffer.open(ev.device, box[0], nbytes)
+    return buf
+
+
+def peer_buffer_bytes(ev, B, staged=True):
+    """bytes of the gathering rank's buffer: F rows | G rows | (staged) compact rows of the peers"""
+    from .evaluator import padded_ld
+    ldF, ldG, ldC = padded_ld(ev.neF), padded_ld(ev.neG), padded_ld(ev.compact_len)
+    return 8 * B * (ldF + ldG + (ldC if staged else 0))

@@ -114,6 +114,58 @@ def expand_compact_g(mission, ts, Gc, G=None, threads=0):
     return G
 
 
+IPC_HANDLE_BYTES = 64
+
+
+class PeerBuffer:
+    """Device memory other GPUs of the box can write (include/tolcuda.h, "result buffers that other GPUs
+    write directly").  PeerBuffer.alloc on the gathering rank, .handle sent to the others, PeerBuffer.open
+    there.  .ptr is the address valid on `device`; .tensor(...) views the owner's allocation as a torch tensor."""
+
+    def __init__(self, device, ptr, nbytes, owner, handle=None):
+        self.device, self.ptr, self.nbytes, self.owner, self.handle = device, ptr, nbytes, owner, handle
+
+    @classmethod
+    def alloc(cls, device, nbytes):
+        L = _l.load()
+        p = C.c_void_p()
+        _l.check(L.tolcuda_device_alloc(int(device), int(nbytes), C.byref(p)))
+        h = C.create_string_buffer(IPC_HANDLE_BYTES)
+        rc = L.tolcuda_ipc_export(int(device), p, h)
+        if rc:
+            L.tolcuda_device_free(int(device), p)
+            _l.check(rc)
+        return cls(device, p.value, nbytes, True, h.raw)
+
+    @classmethod
+    def open(cls, device, handle, nbytes):
+        p = C.c_void_p()
+        _l.check(_l.load().tolcuda_ipc_open(int(device), handle, C.byref(p)))
+        return cls(device, p.value, nbytes, False, handle)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            ptr, self.ptr = self.ptr, None
+            L = _l.load()
+            (L.tolcuda_device_free if self.owner else L.tolcuda_ipc_close)(int(self.device), C.c_void_p(ptr))
+
+    __del__ = close
+
+    def tensor(self, offset_doubles, rows, ld):
+        """[rows, ld] float64 torch view of the allocation, starting `offset_doubles` in (the tensor keeps
+        this object alive)"""
+        import torch
+        assert 8 * (offset_doubles + rows * ld) <= self.nbytes
+
+        class _View:
+            pass
+        v = _View()
+        v.keep = self
+        v.__cuda_array_interface__ = {"shape": (rows, ld), "typestr": "<f8", "version": 2, "strides": None,
+                                      "data": (self.ptr + 8 * offset_doubles, False)}
+        return torch.as_tensor(v, device=torch.device("cuda", self.device))
+
+
 class Evaluator:
     def __init__(self, mission, ts, aircraft, gains, goal_ned, wind_model=1, device=0):
         L = _l.load()
@@ -229,6 +281,14 @@ class Evaluator:
         flags |= (int(needG) >> 1) << 16  # experiment switches (tools/kbench.py)
         _l.check(self.L.tolcuda_eval_batch(self.h, B, X.data_ptr(), X.stride(0), F.data_ptr(), F.stride(0),
                                            G.data_ptr(), G.stride(0), flags))
+
+    def eval_batch_ptrs(self, B, x_ptr, ldx, F_ptr, ldF, G_ptr, ldG, needF=True, needG=True, sync=True,
+                        compact_rows=False):
+        """tolcuda_eval_batch with raw device addresses (integers): F_ptr / G_ptr may lie in a peer GPU's memory
+        (PeerBuffer), x_ptr on this context's device"""
+        flags = (NEED_F if needF else 0) | (NEED_G if needG else 0) | DEVICE_PTRS | (0 if sync else NO_SYNC)
+        flags |= COMPACT_G if compact_rows else 0
+        _l.check(self.L.tolcuda_eval_batch(self.h, int(B), x_ptr, int(ldx), F_ptr, int(ldF), G_ptr, int(ldG), flags))
 
     def expand_compact_device(self, Gc, G, sync=True):
         """tolcuda_expand_compact_g_device: compact rows (torch CUDA tensor [B, >= compact_len]) -> rows in

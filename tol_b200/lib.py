@@ -60,6 +60,12 @@ def load():
     L.tolcuda_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.tolcuda_host_free.argtypes = [vp]
     L.tolcuda_device_count.argtypes = [ip]
+    L.tolcuda_device_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp)]
+    L.tolcuda_device_free.argtypes = [C.c_int, vp]
+    L.tolcuda_ipc_export.argtypes = [C.c_int, vp, C.c_char_p]
+    L.tolcuda_ipc_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]
+    L.tolcuda_ipc_close.argtypes = [C.c_int, vp]
+    L.tolcuda_enable_peer.argtypes = [C.c_int, C.c_int]
     L.tolcuda_padded_ld.argtypes = [C.c_long]
     L.tolcuda_padded_ld.restype = C.c_long
     L.tolcuda_set_stream.argtypes = [vp, vp]
