@@ -705,3 +705,28 @@ def test_shards_written_into_one_gpu_over_nvlink(name, B, compact, tmp_path):
     ev.close()
     assert np.array_equal(got["F"].view(np.int64), F.view(np.int64))
     assert np.array_equal(got["G"].view(np.int64), G.view(np.int64))
+
+
+def test_one_process_two_devices_peer_rows():
+    """2+ GPUs in ONE process (tolbatch's shape): after tolcuda_enable_peer(1, 0) the context of device 1 writes
+    its F/G rows into a buffer that lives on device 0; bit-identical to device 0 evaluating the same rows"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from tol_b200 import lib as _l
+    g = load_golden("G7_skywalker_ts100")
+    B = 23
+    X = T.synth.batch(g["x"][0], 31337, 0, B)
+    ev0, ev1 = T.Evaluator.from_golden(g, device=0), T.Evaluator.from_golden(g, device=1)
+    ldF, ldG = T.evaluator.padded_ld(ev0.neF), T.evaluator.padded_ld(ev0.neG)
+    _l.check(_l.load().tolcuda_enable_peer(1, 0))
+    _l.check(_l.load().tolcuda_enable_peer(1, 0))  # idempotent
+    buf = T.PeerBuffer.alloc(0, 8 * B * (ldF + ldG))
+    X1 = torch.from_numpy(X).to("cuda:1")
+    ev1.eval_batch_ptrs(B, X1.data_ptr(), X1.stride(0), buf.ptr, ldF, buf.ptr + 8 * B * ldF, ldG)
+    F, G = buf.tensor(0, B, ldF), buf.tensor(B * ldF, B, ldG)
+    Fd = torch.empty(B, ev0.neF, dtype=torch.float64, device="cuda:0")
+    Gd = torch.empty(B, ev0.neG, dtype=torch.float64, device="cuda:0")
+    ev0.eval_batch_device(torch.from_numpy(X).to("cuda:0"), Fd, Gd)
+    assert torch.equal(F[:, :ev0.neF], Fd) and torch.equal(G[:, :ev0.neG], Gd)
+    del F, G
+    ev0.close(), ev1.close(), buf.close()
