@@ -185,6 +185,20 @@ int tolcuda_expand_compact_g_device(tolcuda_handle h, long B, const double *Gc, 
  * Gcsc[b*ldC + p] = G[b*ldG + perm[p]], on the context's stream (flags: 0 or TOLCUDA_NO_SYNC). */
 int tolcuda_problem_pattern_csc(int formulation, int ts, int *colptr, int *rowidx, int *perm);
 int tolcuda_repack_csc_device(tolcuda_handle h, long B, const double *G, long ldG, double *Gcsc, long ldC, int flags);
+/* Matrix-free products with the Jacobian (a device-side consumer of G for an iterative QP / SQP step on the GPU;
+ * SURVEY.md 8f-4, nothing of the kind in the reference): J(x_b) is the neF x n matrix whose coordinate entries
+ * (tolcuda_pattern) are the G values tolcuda_eval_batch writes for x_b.  The kernels evaluate every window's
+ * entries exactly as for G and consume them in registers -- G is never written, so a product moves
+ * 8*(2n + neF) bytes per trajectory instead of 8*(n + neF + neG).
+ *   tolcuda_jac_vec    y[b*ldy + i] = sum_j J_ij d[b*ldd + j]        d: n per row,   y: neF per row
+ *   tolcuda_jac_tvec   z[b*ldz + j] = sum_i J_ij lambda[b*ldl + i]   lambda: neF,    z: n
+ * Device pointers on the context's device; flags: 0 or TOLCUDA_NO_SYNC.  Sums run in ascending column (row)
+ * order within a window, separately rounded products (no FMA contraction); they agree with products formed from
+ * the G rows to rounding of the sums (tests/test_gpu_parity.py::test_matrix_free_jacobian_products). */
+int tolcuda_jac_vec(tolcuda_handle h, int B, const double *x, long ldx, const double *d, long ldd, double *y, long ldy,
+                    int flags);
+int tolcuda_jac_tvec(tolcuda_handle h, int B, const double *x, long ldx, const double *lambda, long ldl, double *z,
+                     long ldz, int flags);
 /* host threads the host-pointer batch path of this context expands compact rows with (0 = default:
  * environment TOLCUDA_HOST_THREADS, else the cores available to the process / LOCAL_WORLD_SIZE) */
 int tolcuda_set_host_threads(tolcuda_handle h, int threads);

@@ -41,6 +41,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <utility>
 
 #include "fg_const.h"
 #include "fg_launch.h"
@@ -83,6 +84,63 @@ constexpr int NVAR = TOLCUDA_NVAR;     // x-dependent entries of a record (plus 
 // NVAR x-dependent entries of every window, then the boundary block) for the host-pointer path, where the
 // structural constants are filled in on the host instead of crossing PCIe
 constexpr int MODE_PLAIN = 0, MODE_SUMMARY = 1, MODE_COMPACT = 2;
+// matrix-free consumers of the Jacobian (G is never written): MODE_JVP  y = J(x) d  (the F pointer
+// receives y, the G pointer holds d), MODE_VJP  z = J(x)^T lambda  (the F pointer holds lambda, the G pointer receives z)
+constexpr int MODE_JVP = 3, MODE_VJP = 4;
+__host__ __device__ constexpr bool mode_is_op(int mode) { return mode == MODE_JVP || mode == MODE_VJP; }
+
+// What record position p (row s = p / 13, column j = p % 13: 0 = dt, 1..11 = component j-1 of node k, 12 =
+// component s of node k+1) holds: >= 0 index into the window's NVAR x-dependent values (the positions
+// record_store writes), -1: 0, -2: +1, -3: -1, -4: -dt (the positions tile_init / record_store write)
+__host__ __device__ constexpr int rec_kind(int p) {
+    constexpr int pos[TOLCUDA_NVAR] = {0,  4,  5,  6,  13, 17, 18, 19, 26, 30, 31, 39, 43, 44, 45, 47,
+                                       50, 52, 56, 57, 58, 59, 60, 65, 69, 70, 71, 72, 73, 78, 91};
+    for (int i = 0; i < TOLCUDA_NVAR; i++)
+        if (pos[i] == p) return i;
+    if (p == 1 || p == 15 || p == 29 || p == 85 || p == 99) return -3;
+    if (p % 13 == 12) return -2;
+    if (p == 87 || p == 101) return -4;
+    return -1;
+}
+template <int P>
+__device__ __forceinline__ double rec_value(const double *v, const double mdt) {
+    constexpr int kd = rec_kind(P);
+    if constexpr (kd >= 0) return v[kd];
+    else if constexpr (kd == -2) return 1.0;
+    else if constexpr (kd == -3) return -1.0;
+    else if constexpr (kd == -4) return mdt;
+    else return 0.0;
+}
+// acc + R[P] * w, skipping structural zeros and multiplications by +-1
+template <int P>
+__device__ __forceinline__ double rec_madd(const double acc, const double *v, const double mdt, const double w) {
+    constexpr int kd = rec_kind(P);
+    if constexpr (kd == -1) return acc;
+    else if constexpr (kd == -2) return acc + w;
+    else if constexpr (kd == -3) return acc - w;
+    else return acc + rec_value<P>(v, mdt) * w;
+}
+// row S of a window's record times dv[0..12]; column J of it times lam[0..7]
+template <int S, int... J>
+__device__ __forceinline__ double rec_row_dot(const double *v, const double mdt, const double *dv, std::integer_sequence<int, J...>) {
+    double a = 0.0;
+    ((a = rec_madd<13 * S + J>(a, v, mdt, dv[J])), ...);
+    return a;
+}
+template <int J, int... S>
+__device__ __forceinline__ double rec_col_dot(const double *v, const double mdt, const double *lam, std::integer_sequence<int, S...>) {
+    double a = 0.0;
+    ((a = rec_madd<13 * S + J>(a, v, mdt, lam[S])), ...);
+    return a;
+}
+template <int... S>
+__device__ __forceinline__ void rec_times_vec(const double *v, const double mdt, const double *dv, double *y, std::integer_sequence<int, S...>) {
+    ((y[S] = rec_row_dot<S>(v, mdt, dv, std::make_integer_sequence<int, 12>())), ...);  // column 12 (+1) by the caller
+}
+template <int... J>
+__device__ __forceinline__ void rec_transposed_times_vec(const double *v, const double mdt, const double *lam, double *z, std::integer_sequence<int, J...>) {
+    ((z[J] = rec_col_dot<J>(v, mdt, lam, std::make_integer_sequence<int, TOLCUDA_PF>())), ...);
+}
 
 // per-lane partial results a tile hands back: cost sums and the feasibility summary of its defects
 struct TileSums {
@@ -301,8 +359,14 @@ template <int FORM, int WIND, int MODE>
 __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *tile, const uint32_t tile_s, const double dt,
                                           const int k0, const int nk, const int lane,
                                           double *__restrict__ Fb, double *__restrict__ Gb,
-                                          const int needF, const int needG, TileSums &ts_out) {
+                                          const int needF, const int needG, TileSums &ts_out,
+                                          const double *aux = nullptr) {
     double &sumT = ts_out.sumT, &sump = ts_out.sump;
+    constexpr bool OP = mode_is_op(MODE);
+    if (MODE == MODE_JVP) {  // the window's slice of d (the G pointer) into the unused record buffer
+        slice_prefetch(tile_s, Gb + (size_t)PX * k0, 1 + PX * (nk + 1), lane);
+        cp_async_commit();
+    }
     constexpr bool X3 = (WIND == 3);             // wind cube: Wx with all three gradient components
     constexpr bool W = (WIND == 1) || X3;        // Wx and dWx/dz present
     constexpr bool S10 = (FORM == TOLCUDA_FORM_S10);
@@ -443,7 +507,7 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
     }
     __syncwarp();  // every lane has read its window: the slice is dead, sx becomes the staging area
 
-    if (needF) {
+    if (needF && !OP) {
         double *fs = sx + F_LD * lane;
         st2(fs + 0, f[0], f[1]);
         st2(fs + 2, f[2], f[3]);
@@ -460,7 +524,8 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
     }
     if (!needG) return;
 
-    if (S10) {
+    if (OP) {
+    } else if (S10) {
         // objective row [dt, (x, y, T) of every node]: this warp's 3*nk (+3) entries
         if (active) {
             sx[3 * lane] = r0x;
@@ -545,6 +610,88 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
     }
     v[29] = -dphi;  // F7 :1172
     v[30] = -dCL;   // F8 :1184
+    }
+
+    if (MODE == MODE_JVP) {
+        // y = J d for this warp's rows: the window's 8 defect rows (src/problem.cpp:1074-1192 entries times the
+        // matching d components, columns in ascending order) leave like F; the objective row's share of this
+        // tile (src/problemS10.cpp:340-372, src/problemG7.cpp:370) goes back through sumT
+        cp_async_wait<0>();
+        __syncwarp();
+        const double *d0 = tile + 1 + PX * (active ? lane : 0);
+        double dv[12], y[PF];
+#pragma unroll
+        for (int j = 0; j < PX; j++) dv[1 + j] = d0[j];
+        dv[0] = __ldg(Gb);
+        const double dTe = d0[PX + 10], dxe = d0[PX], dye = d0[PX + 1];
+        double part = 0.0;
+        if (active) part = S10 ? r0x * dv[1] + r0y * dv[2] + (c.kT * T) * dv[11] : (c.kT * T) * dv[11];
+        if (last_window) part += S10 ? rex * dxe + rey * dye + (c.kT * Te) * dTe : (c.kT * Te) * dTe;
+        sumT = part;
+        // the last column of row s multiplies component s of node k+1
+        double acc[PF];
+        rec_times_vec(v, mdt, dv, acc, std::make_integer_sequence<int, PF>());
+#pragma unroll
+        for (int s2 = 0; s2 < PF; s2++) y[s2] = acc[s2] + d0[PX + s2];
+        __syncwarp();
+        double *fs = sx + F_LD * lane;
+        st2(fs + 0, y[0], y[1]);
+        st2(fs + 2, y[2], y[3]);
+        st2(fs + 4, y[4], y[5]);
+        st2(fs + 6, y[6], y[7]);
+        __syncwarp();
+        double *dst = Fb + 1 + PF * k0;
+#pragma unroll
+        for (int it = 0; it < PF; it++) {
+            const int i = lane + 32 * it;
+            if (i < PF * nk) dst[i] = sx[F_LD * (i >> 3) + (i & 7)];
+        }
+        __syncwarp();
+        return;
+    }
+    if (MODE == MODE_VJP) {
+        // z = J^T lambda for this warp's nodes: node k collects its own window's columns, the +1 entries of
+        // window k-1 (component c of node k appears in row c of window k-1 with value 1), the objective row's
+        // entries times lambda_0, and -- nodes 0 and ts only -- the boundary rows' share prepared in aux
+        const double *lamrow = Fb;
+        const double lam0 = __ldg(lamrow);
+        double lam[PF], z[12];
+#pragma unroll
+        for (int s2 = 0; s2 < PF; s2++) lam[s2] = active ? __ldg(lamrow + 1 + (size_t)PF * k + s2) : 0.0;
+        rec_transposed_times_vec(v, mdt, lam, z, std::make_integer_sequence<int, 12>());
+        sumT = active ? z[0] : 0.0;  // d/d dt column: summed over the trajectory
+        if (S10) {
+            z[1] += lam0 * r0x;
+            z[2] += lam0 * r0y;
+        }
+        z[11] += lam0 * (c.kT * T);
+        if (active) {
+            double *zs = sx + 1 + PX * lane;
+#pragma unroll
+            for (int j = 0; j < PX; j++) {
+                double zz = z[1 + j];
+                if (j < PF && k > 0) zz += __ldg(lamrow + 1 + (size_t)PF * (k - 1) + j);
+                if (k == 0) zz += aux[j];
+                zs[j] = zz;
+            }
+        }
+        if (last_window) {
+            double *ze = sx + 1 + PX * (lane + 1);
+#pragma unroll
+            for (int j = 0; j < PX; j++) {
+                double zz = j < PF ? lam[j < PF ? j : 0] : 0.0;
+                if (S10 && j == 0) zz += lam0 * rex;
+                if (S10 && j == 1) zz += lam0 * rey;
+                if (j == 10) zz += lam0 * (c.kT * Te);
+                ze[j] = zz + aux[PX + j];
+            }
+        }
+        __syncwarp();
+        const int cntz = PX * nk + ((k0 + nk == ts) ? PX : 0);
+        double *dst = Gb + 1 + (size_t)PX * k0;
+        for (int i = lane; i < cntz; i += 32) dst[i] = sx[1 + i];
+        __syncwarp();
+        return;
     }
 
     if (MODE == MODE_COMPACT) {
@@ -722,6 +869,86 @@ __device__ __forceinline__ void traj_epilogue(const FgConst &c, const int lane, 
     }
 }
 
+// ---- matrix-free operators: the rows / columns of J that touch only dt, node 0 and node ts ------------------------
+//
+// G7's objective-row ends and boundary rows (src/problemG7.cpp:343-380, 404-511) from node 0 / node ts held by
+// lanes < 11 of a whole warp, with the expressions of traj_epilogue
+struct G7Ends {
+    double dist, gx0, gy0, ex, ey;
+};
+__device__ __forceinline__ G7Ends g7_ends(const FgConst &c, const double dt, const double n0, const double ne) {
+    const double x0 = __shfl_sync(0xffffffffu, n0, 0), y0 = __shfl_sync(0xffffffffu, n0, 1);
+    const double xf = __shfl_sync(0xffffffffu, ne, 0), yf = __shfl_sync(0xffffffffu, ne, 1);
+    const double ddx = xf - x0, ddy = yf - y0;
+    G7Ends e;
+    e.dist = sqrt(ddx * ddx + ddy * ddy);
+    const double d3 = e.dist * e.dist * e.dist;
+    e.gx0 = c.kp_ts * dt * ddx / d3, e.gy0 = c.kp_ts * dt * ddy / d3;
+    e.ex = ddx / e.dist, e.ey = ddy / e.dist;
+    return e;
+}
+
+// MODE_VJP, before the tiles run: what lambda_0 (G7 objective-row ends) and the boundary rows' multipliers add to
+// z at node 0 (aux[0..10]) and node ts (aux[11..21]); executed by one whole warp
+template <int FORM>
+__device__ __forceinline__ void op_aux(const FgConst &c, const int lane, const double dt, const double n0, const double ne,
+                                       const double *__restrict__ lamrow, double *aux) {
+    const double lb = lane < c.nb ? __ldg(lamrow + (c.neF - c.nb) + lane) : 0.0;
+    double a0 = -lb, a1 = lb;  // rows [dt: 0, (0,c): -1, (ts,c): +1], src/problemS10.cpp:395-415, src/problemG7.cpp:404-511
+    if (FORM == TOLCUDA_FORM_G7) {
+        const double lam0 = __ldg(lamrow);
+        const G7Ends e = g7_ends(c, dt, n0, ne);
+        const double lb0 = __shfl_sync(0xffffffffu, lb, 0), lb1 = __shfl_sync(0xffffffffu, lb, 1);
+        const double lb11 = __shfl_sync(0xffffffffu, lb, 11);
+        const double cd = c.cos_chid, sd = c.sin_chid;
+        if (lane == 0) {
+            a0 = lam0 * e.gx0 + lb0 * (-1.0 + e.ex * cd) + lb1 * (e.ex * sd) + lb11 * (-e.ex);
+            a1 = lam0 * (-e.gx0) + lb0 * (1.0 - e.ex * cd) + lb1 * (-(e.ex * sd)) + lb11 * e.ex;
+        } else if (lane == 1) {
+            a0 = lam0 * e.gy0 + lb0 * (e.ey * cd) + lb1 * (-1.0 + e.ey * sd) + lb11 * (-e.ey);
+            a1 = lam0 * (-e.gy0) + lb0 * (-(e.ey * cd)) + lb1 * (1.0 - e.ey * sd) + lb11 * e.ey;
+        }
+    }
+    if (lane < PX) aux[lane] = a0, aux[PX + lane] = a1;
+}
+
+// end of a trajectory in the operator modes, one whole warp; tot: the trajectory's sum of the tiles' shares
+// (MODE_JVP: objective-row entries times d; MODE_VJP: the d/d dt column times lambda)
+template <int FORM, int MODE>
+__device__ __forceinline__ void op_epilogue(const FgConst &c, const int lane, const double dt, const double tot,
+                                            const double n0, const double ne, double *__restrict__ Fb,
+                                            double *__restrict__ Gb) {
+    constexpr bool S10 = (FORM == TOLCUDA_FORM_S10);
+    const int ts = c.ts;
+    if (MODE == MODE_JVP) {  // Fb: y (out), Gb: d (in)
+        const double ddt = __ldg(Gb);
+        double d0 = 0.0, de = 0.0;
+        if (lane < PX) d0 = __ldg(Gb + 1 + lane), de = __ldg(Gb + 1 + (size_t)PX * ts + lane);
+        double *ybnd = Fb + (c.neF - c.nb);
+        if (S10) {
+            if (lane == 0) Fb[0] = c.kdt * ddt + tot;
+            if (lane < PX) ybnd[lane] = de - d0;
+        } else {
+            const G7Ends e = g7_ends(c, dt, n0, ne);
+            const double d0x = __shfl_sync(0xffffffffu, d0, 0), d0y = __shfl_sync(0xffffffffu, d0, 1);
+            const double dex = __shfl_sync(0xffffffffu, de, 0), dey = __shfl_sync(0xffffffffu, de, 1);
+            const double cd = c.cos_chid, sd = c.sin_chid;
+            if (lane == 0) {
+                Fb[0] = (c.kp_ts / e.dist) * ddt + e.gx0 * d0x + e.gy0 * d0y + tot + (-e.gx0) * dex + (-e.gy0) * dey;
+                ybnd[0] = (-1.0 + e.ex * cd) * d0x + (e.ey * cd) * d0y + (1.0 - e.ex * cd) * dex + (-(e.ey * cd)) * dey;
+                ybnd[1] = (e.ex * sd) * d0x + (-1.0 + e.ey * sd) * d0y + (-(e.ex * sd)) * dex + (1.0 - e.ey * sd) * dey;
+                ybnd[11] = (-e.ex) * d0x + (-e.ey) * d0y + e.ex * dex + e.ey * dey;
+            }
+            if (lane >= 2 && lane < PX) ybnd[lane] = de - d0;
+        }
+    } else {  // Fb: lambda (in), Gb: z (out)
+        const double lam0 = __ldg(Fb);
+        double row0dt = c.kdt;
+        if (!S10) row0dt = c.kp_ts / g7_ends(c, dt, n0, ne).dist;
+        if (lane == 0) Gb[0] = tot + lam0 * row0dt;
+    }
+}
+
 // ---- kernel A: one CTA per run of `per` consecutive trajectories ------------------------------------------------
 //
 // blockDim.x = 32*ceil(ts/32) (<= MAXT).  Warp w owns windows 32w..32w+31 of every trajectory of the run and
@@ -740,8 +967,10 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int B, int per_arg, const doubl
                double *__restrict__ S, long ldS) {
     constexpr bool SUMM = (MODE == MODE_SUMMARY);
     extern __shared__ __align__(16) double smem[];
+    constexpr bool OP = mode_is_op(MODE);
     __shared__ double red[MAXPER][SUMM ? 4 : 2][32];
     __shared__ int arrivals[MAXPER];
+    __shared__ double opaux[OP ? 2 * PX : 1];
     const int ts = c.ts;
     const int tid = thread_index();
     // the warp index through a shuffle from lane 0: provably warp-uniform, so everything derived from it
@@ -768,8 +997,9 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int B, int per_arg, const doubl
         n0_nx = __ldg(xw - (size_t)PX * k0 + 1 + lane);
         ne_nx = __ldg(xw - (size_t)PX * k0 + (size_t)PX * ts + 1 + lane);
     }
-    if (needG) tile_init(tile, lane);
+    if (needG && !OP) tile_init(tile, lane);
     if (tid < MAXPER) arrivals[tid] = 0;
+    if (MODE == MODE_VJP && warp == 0) op_aux<FORM>(c, lane, dt_nx, n0_nx, ne_nx, F + b0 * ldF, opaux);  // LOOP = false
     __syncthreads();
 #pragma unroll 1
     for (int t = 0; t < ntraj; t++) {
@@ -791,7 +1021,8 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int B, int per_arg, const doubl
         __syncwarp();
         double *Fb = F + b * ldF, *Gb = G + b * ldG;
         TileSums tsum;
-        tile_eval<FORM, WIND, MODE>(c, wsm + slot * SX_LEN, tile, tile_s, dt, k0, nk, lane, Fb, Gb, needF, needG, tsum);
+        tile_eval<FORM, WIND, MODE>(c, wsm + slot * SX_LEN, tile, tile_s, dt, k0, nk, lane, Fb, Gb, needF, needG, tsum,
+                                    OP ? opaux : nullptr);
         __syncwarp();
         const double sumT = warp_sum(tsum.sumT);
         const double sump = FORM == TOLCUDA_FORM_S10 ? warp_sum(tsum.sump) : 0.0;
@@ -820,8 +1051,11 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int B, int per_arg, const doubl
                     dssq += vred[96 + w];
                 }
             }
-            traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG, dmax, dssq,
-                                SUMM ? S + b * ldS : nullptr, MODE == MODE_COMPACT ? NVAR : REC);
+            if (OP)
+                op_epilogue<FORM, MODE>(c, lane, dt, tT, n0, ne, Fb, Gb);
+            else
+                traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG, dmax, dssq,
+                                    SUMM ? S + b * ldS : nullptr, MODE == MODE_COMPACT ? NVAR : REC);
         }
     }
     cp_async_wait<0>();
@@ -843,8 +1077,10 @@ fg_long_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, 
                double *__restrict__ S, long ldS) {
     constexpr bool SUMM = (MODE == MODE_SUMMARY);
     extern __shared__ __align__(16) double smem[];
+    constexpr bool OP = mode_is_op(MODE);
     __shared__ double red[SUMM ? 4 : 2][32];
     __shared__ int arrivals;
+    __shared__ double opaux[OP ? 2 * PX : 1];
     const int ts = c.ts;
     const int nt = (ts + 31) >> 5;
     const int tid = thread_index();
@@ -863,8 +1099,9 @@ fg_long_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, 
         n0 = __ldg(xb + 1 + lane);
         ne = __ldg(xb + (size_t)PX * ts + 1 + lane);
     }
-    if (needG) tile_init(tile, lane);
+    if (needG && !OP) tile_init(tile, lane);
     if (tid == 0) arrivals = 0;
+    if (MODE == MODE_VJP && warp == 0) op_aux<FORM>(c, lane, dt, n0, ne, Fb, opaux);
     __syncthreads();
     double accT = 0.0, accp = 0.0, accm = 0.0, accq = 0.0;
     int slot = 0;
@@ -878,7 +1115,7 @@ fg_long_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, 
         __syncwarp();
         TileSums tsum;
         tile_eval<FORM, WIND, MODE>(c, wsm + slot * SX_LEN, tile, tile_s, dt, 32 * j, min(32, ts - 32 * j), lane, Fb, Gb,
-                                    needF, needG, tsum);
+                                    needF, needG, tsum, OP ? opaux : nullptr);
         __syncwarp();
         accT += tsum.sumT;
         accp += tsum.sump;
@@ -914,8 +1151,11 @@ fg_long_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, 
             dssq += vred[96 + w];
         }
     }
-    traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG, dmax, dssq, SUMM ? S + b * ldS : nullptr,
-                        MODE == MODE_COMPACT ? NVAR : REC);
+    if (OP)
+        op_epilogue<FORM, MODE>(c, lane, dt, tT, n0, ne, Fb, Gb);
+    else
+        traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG, dmax, dssq, SUMM ? S + b * ldS : nullptr,
+                            MODE == MODE_COMPACT ? NVAR : REC);
 }
 
 template <int FORM, int WIND, int MAXT, int MINB, int MODE, bool LOOP>
@@ -964,6 +1204,15 @@ cudaError_t launch_long(const FgLaunch &L) {
     return cudaGetLastError();
 }
 
+// the operator modes always take one trajectory per CTA (straight-line instance)
+template <int FORM, int WIND, int MODE>
+cudaError_t launch_op(const FgLaunch &L) {
+    const int ts = L.c->ts;
+    if (L.kernel == 2 || ts > 256) return launch_long<FORM, WIND, MODE>(L);
+    if (ts <= 128) return launch_cta_as<FORM, WIND, 128, 4, MODE, false>(L, 1);
+    return launch_cta_as<FORM, WIND, 256, 2, MODE, false>(L, 1);
+}
+
 template <int FORM, int WIND, int MODE>
 cudaError_t launch_sel(const FgLaunch &L) {
     // Kernel A needs the whole trajectory in one CTA with one tile per warp: ts <= 256.  Longer trajectories,
@@ -977,6 +1226,8 @@ cudaError_t launch_sel(const FgLaunch &L) {
 // the per-trajectory summary is a separate instantiation so that plain F/G launches pay nothing for it
 template <int FORM, int WIND>
 cudaError_t launch_any(const FgLaunch &L) {
+    if (L.op == 1) return launch_op<FORM, WIND, MODE_JVP>(L);
+    if (L.op == 2) return launch_op<FORM, WIND, MODE_VJP>(L);
     if (L.compact) return launch_sel<FORM, WIND, MODE_COMPACT>(L);
     return L.S ? launch_sel<FORM, WIND, MODE_SUMMARY>(L) : launch_sel<FORM, WIND, MODE_PLAIN>(L);
 }

@@ -21,6 +21,7 @@ struct FgLaunch {
     int needF, needG;
     double *S;  // optional per-trajectory summary [B][ldS >= 4]: objective, max|defect|, max|boundary|, sum defect^2
     long ldS;
+    int op;  // 0: F/G; 1: y = J d (F receives y [neF], G holds d [n]); 2: z = J^T lambda (F holds lambda [neF], G receives z [n])
     int compact;  // G/ldG address the compact layout [R0 | 31 per window | boundary block] (host-pointer path)
     int kernel;    // 0/1 = kernel A (CTA per run of trajectories), 2 = kernel L (CTA per trajectory, tile loop; any ts)
     int per;       // kernel A: trajectories per CTA (1..4)

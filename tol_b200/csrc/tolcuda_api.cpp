@@ -81,10 +81,11 @@ tolcuda_ctx *g_bound = nullptr;
 long round_up(long v, long m) { return (v + m - 1) / m * m; }
 
 int launch(tolcuda_ctx *h, cudaStream_t st, int B, const double *x, long ldx, double *F, long ldF,
-           double *G, long ldG, int needF, int needG, double *S = nullptr, long ldS = 0, int compact = 0) {
+           double *G, long ldG, int needF, int needG, double *S = nullptr, long ldS = 0, int compact = 0, int op = 0) {
     FgLaunch L{};
     L.S = S, L.ldS = ldS;
     L.compact = compact;
+    L.op = op;
     L.c = &h->c;
     L.B = B;
     L.x = x, L.ldx = ldx, L.F = F, L.ldF = ldF, L.G = G, L.ldG = ldG;
@@ -690,6 +691,40 @@ int tolcuda_expand_compact_g_device(tolcuda_handle h, long B, const double *Gc, 
     h->launches += B > 0 ? (B + 65534) / 65535 : 0;
     if (!(flags & TOLCUDA_NO_SYNC)) CU(cudaStreamSynchronize(h->stream));
     return 0;
+}
+
+// y = J(x) d and z = J(x)^T lambda without materialising G (fg_kernels.cu, MODE_JVP / MODE_VJP)
+static int jac_op(tolcuda_handle h, int op, int B, const double *x, long ldx, const double *in, long ldin, long len_in,
+                  double *out, long ldout, long len_out, int flags, const char *who) {
+    if (!h || B < 0) return TOLCUDA_EINVAL;
+    if (B == 0) return 0;
+    const FgConst &c = h->c;
+    if (!x || !in || !out || ldx < c.n || ldin < len_in || ldout < len_out) {
+        set_error(std::string(who) + ": null pointer or leading dimension shorter than the row");
+        return TOLCUDA_EINVAL;
+    }
+    if (flags & TOLCUDA_HOST_PTRS) {
+        set_error(std::string(who) + ": device pointers only");
+        return TOLCUDA_EUNSUPPORTED;
+    }
+    CU(cudaSetDevice(h->cfg.device));
+    // op 1: the F pointer receives y, the G pointer holds d; op 2: the F pointer holds lambda, the G pointer receives z
+    double *Fp = op == 1 ? out : const_cast<double *>(in), *Gp = op == 1 ? const_cast<double *>(in) : out;
+    const long ldFp = op == 1 ? ldout : ldin, ldGp = op == 1 ? ldin : ldout;
+    int rc = launch(h, h->stream, B, x, ldx, Fp, ldFp, Gp, ldGp, 1, 1, nullptr, 0, 0, op);
+    if (rc) return rc;
+    if (!(flags & TOLCUDA_NO_SYNC)) CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int tolcuda_jac_vec(tolcuda_handle h, int B, const double *x, long ldx, const double *d, long ldd, double *y, long ldy,
+                    int flags) {
+    return jac_op(h, 1, B, x, ldx, d, ldd, h ? h->c.n : 0, y, ldy, h ? h->c.neF : 0, flags, "tolcuda_jac_vec");
+}
+
+int tolcuda_jac_tvec(tolcuda_handle h, int B, const double *x, long ldx, const double *lambda, long ldl, double *z,
+                     long ldz, int flags) {
+    return jac_op(h, 2, B, x, ldx, lambda, ldl, h ? h->c.neF : 0, z, ldz, h ? h->c.n : 0, flags, "tolcuda_jac_tvec");
 }
 
 int tolcuda_problem_pattern_csc(int formulation, int ts, int *colptr, int *rowidx, int *perm) {

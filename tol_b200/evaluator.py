@@ -301,6 +301,17 @@ class Evaluator:
         _l.check(self.L.tolcuda_repack_csc_device(self.h, G.shape[0], G.data_ptr(), G.stride(0), Gcsc.data_ptr(),
                                                   Gcsc.stride(0), 0 if sync else NO_SYNC))
 
+    def jac_vec(self, X, D, Y, sync=True):
+        """tolcuda_jac_vec: Y[b] = J(X[b]) D[b] without materialising G (torch CUDA tensors [B, >= n], [B, >= n],
+        [B, >= neF])"""
+        _l.check(self.L.tolcuda_jac_vec(self.h, X.shape[0], X.data_ptr(), X.stride(0), D.data_ptr(), D.stride(0),
+                                        Y.data_ptr(), Y.stride(0), 0 if sync else NO_SYNC))
+
+    def jac_tvec(self, X, Lam, Z, sync=True):
+        """tolcuda_jac_tvec: Z[b] = J(X[b])^T Lam[b] (torch CUDA tensors [B, >= n], [B, >= neF], [B, >= n])"""
+        _l.check(self.L.tolcuda_jac_tvec(self.h, X.shape[0], X.data_ptr(), X.stride(0), Lam.data_ptr(), Lam.stride(0),
+                                         Z.data_ptr(), Z.stride(0), 0 if sync else NO_SYNC))
+
     def summary_host(self, X, needF=False, needG=False):
         """tolcuda_eval_batch_summary with host arrays: [B, 4] = objective, max|defect|, max boundary
         violation, sum defect^2 (F and G are not produced unless asked for)"""

@@ -32,6 +32,13 @@ for name in ("S10_tempest_ts200", "G7_skywalker_ts100", "S10_tempest_ts100_wind3
         Gc = torch.empty(B, ev.compact_len, dtype=torch.float64, device="cuda")
         ev.eval_batch_device(Xd, Fd, Gc, compact_rows=True)
         ev.expand_compact_device(Gc, Gd)
+        D = torch.rand(B, ev.n, dtype=torch.float64, device="cuda")
+        Lam = torch.rand(B, ev.neF, dtype=torch.float64, device="cuda")
+        Y, Z = torch.empty(B, ev.neF, dtype=torch.float64, device="cuda"), torch.empty(B, ev.n, dtype=torch.float64, device="cuda")
+        ev.jac_vec(Xd, D, Y)
+        ev.jac_tvec(Xd, Lam, Z)
+        lhs, rhs = (Lam * Y).sum(1), (Z * D).sum(1)
+        assert torch.allclose(lhs, rhs, rtol=1e-9, atol=1e-9)
         f1, g1 = ev.eval(X[0])
         assert np.array_equal(G, G2) and np.array_equal(f1, F[0]) and np.array_equal(Gd.cpu().numpy()[:, :ev.neG], G)
         ev.close()
