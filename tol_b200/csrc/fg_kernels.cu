@@ -367,6 +367,13 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
         slice_prefetch(tile_s, Gb + (size_t)PX * k0, 1 + PX * (nk + 1), lane);
         cp_async_commit();
     }
+    constexpr int LAM_OFF = 32;  // MODE_VJP: the record buffer holds aux (22 doubles), then the tile's multipliers
+    if (MODE == MODE_VJP) {
+        // lambda of window k0-1 (its +1 entries reach this tile's first node) and of the tile's own windows: 8 each
+        if (k0 > 0) slice_prefetch(tile_s + 8 * LAM_OFF, Fb + 1 + (size_t)PF * (k0 - 1), PF * (nk + 1), lane);
+        else slice_prefetch(tile_s + 8 * (LAM_OFF + PF), Fb + 1, PF * nk, lane);
+        cp_async_commit();
+    }
     constexpr bool X3 = (WIND == 3);             // wind cube: Wx with all three gradient components
     constexpr bool W = (WIND == 1) || X3;        // Wx and dWx/dz present
     constexpr bool S10 = (FORM == TOLCUDA_FORM_S10);
@@ -655,9 +662,12 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
         // entries times lambda_0, and -- nodes 0 and ts only -- the boundary rows' share prepared in aux
         const double *lamrow = Fb;
         const double lam0 = __ldg(lamrow);
+        cp_async_wait<0>();
+        __syncwarp();
+        const double *lprev = tile + LAM_OFF + PF * lane;  // multipliers of window k-1, then of window k
         double lam[PF], z[12];
 #pragma unroll
-        for (int s2 = 0; s2 < PF; s2++) lam[s2] = active ? __ldg(lamrow + 1 + (size_t)PF * k + s2) : 0.0;
+        for (int s2 = 0; s2 < PF; s2++) lam[s2] = active ? lprev[PF + s2] : 0.0;
         rec_transposed_times_vec(v, mdt, lam, z, std::make_integer_sequence<int, 12>());
         sumT = active ? z[0] : 0.0;  // d/d dt column: summed over the trajectory
         if (S10) {
@@ -670,7 +680,7 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
 #pragma unroll
             for (int j = 0; j < PX; j++) {
                 double zz = z[1 + j];
-                if (j < PF && k > 0) zz += __ldg(lamrow + 1 + (size_t)PF * (k - 1) + j);
+                if (j < PF && k > 0) zz += lprev[j];
                 if (k == 0) zz += aux[j];
                 zs[j] = zz;
             }
@@ -888,8 +898,9 @@ __device__ __forceinline__ G7Ends g7_ends(const FgConst &c, const double dt, con
     return e;
 }
 
-// MODE_VJP, before the tiles run: what lambda_0 (G7 objective-row ends) and the boundary rows' multipliers add to
-// z at node 0 (aux[0..10]) and node ts (aux[11..21]); executed by one whole warp
+// MODE_VJP, before a tile that owns node 0 or node ts: what lambda_0 (G7 objective-row ends) and the boundary rows'
+// multipliers add to z at node 0 (aux[0..10]) and node ts (aux[11..21]); executed by the tile's whole warp, aux is
+// the warp's own (otherwise unused) record buffer
 template <int FORM>
 __device__ __forceinline__ void op_aux(const FgConst &c, const int lane, const double dt, const double n0, const double ne,
                                        const double *__restrict__ lamrow, double *aux) {
@@ -970,7 +981,6 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int B, int per_arg, const doubl
     constexpr bool OP = mode_is_op(MODE);
     __shared__ double red[MAXPER][SUMM ? 4 : 2][32];
     __shared__ int arrivals[MAXPER];
-    __shared__ double opaux[OP ? 2 * PX : 1];
     const int ts = c.ts;
     const int tid = thread_index();
     // the warp index through a shuffle from lane 0: provably warp-uniform, so everything derived from it
@@ -999,7 +1009,6 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int B, int per_arg, const doubl
     }
     if (needG && !OP) tile_init(tile, lane);
     if (tid < MAXPER) arrivals[tid] = 0;
-    if (MODE == MODE_VJP && warp == 0) op_aux<FORM>(c, lane, dt_nx, n0_nx, ne_nx, F + b0 * ldF, opaux);  // LOOP = false
     __syncthreads();
 #pragma unroll 1
     for (int t = 0; t < ntraj; t++) {
@@ -1021,8 +1030,12 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int B, int per_arg, const doubl
         __syncwarp();
         double *Fb = F + b * ldF, *Gb = G + b * ldG;
         TileSums tsum;
+        if (MODE == MODE_VJP && (k0 == 0 || k0 + nk == ts)) {  // the warps that own node 0 / node ts (warp-uniform)
+            op_aux<FORM>(c, lane, dt, n0, ne, Fb, tile);
+            __syncwarp();
+        }
         tile_eval<FORM, WIND, MODE>(c, wsm + slot * SX_LEN, tile, tile_s, dt, k0, nk, lane, Fb, Gb, needF, needG, tsum,
-                                    OP ? opaux : nullptr);
+                                    OP ? tile : nullptr);
         __syncwarp();
         const double sumT = warp_sum(tsum.sumT);
         const double sump = FORM == TOLCUDA_FORM_S10 ? warp_sum(tsum.sump) : 0.0;
@@ -1080,7 +1093,6 @@ fg_long_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, 
     constexpr bool OP = mode_is_op(MODE);
     __shared__ double red[SUMM ? 4 : 2][32];
     __shared__ int arrivals;
-    __shared__ double opaux[OP ? 2 * PX : 1];
     const int ts = c.ts;
     const int nt = (ts + 31) >> 5;
     const int tid = thread_index();
@@ -1101,7 +1113,6 @@ fg_long_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, 
     }
     if (needG && !OP) tile_init(tile, lane);
     if (tid == 0) arrivals = 0;
-    if (MODE == MODE_VJP && warp == 0) op_aux<FORM>(c, lane, dt, n0, ne, Fb, opaux);
     __syncthreads();
     double accT = 0.0, accp = 0.0, accm = 0.0, accq = 0.0;
     int slot = 0;
@@ -1114,8 +1125,12 @@ fg_long_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, 
         cp_async_wait<1>();
         __syncwarp();
         TileSums tsum;
+        if (MODE == MODE_VJP && (j == 0 || j == nt - 1)) {  // the tiles that own node 0 / node ts (warp-uniform)
+            op_aux<FORM>(c, lane, dt, n0, ne, Fb, tile);
+            __syncwarp();
+        }
         tile_eval<FORM, WIND, MODE>(c, wsm + slot * SX_LEN, tile, tile_s, dt, 32 * j, min(32, ts - 32 * j), lane, Fb, Gb,
-                                    needF, needG, tsum, OP ? opaux : nullptr);
+                                    needF, needG, tsum, OP ? tile : nullptr);
         __syncwarp();
         accT += tsum.sumT;
         accp += tsum.sump;
@@ -1204,14 +1219,6 @@ cudaError_t launch_long(const FgLaunch &L) {
     return cudaGetLastError();
 }
 
-// the operator modes always take one trajectory per CTA (straight-line instance)
-template <int FORM, int WIND, int MODE>
-cudaError_t launch_op(const FgLaunch &L) {
-    const int ts = L.c->ts;
-    if (L.kernel == 2 || ts > 256) return launch_long<FORM, WIND, MODE>(L);
-    if (ts <= 128) return launch_cta_as<FORM, WIND, 128, 4, MODE, false>(L, 1);
-    return launch_cta_as<FORM, WIND, 256, 2, MODE, false>(L, 1);
-}
 
 template <int FORM, int WIND, int MODE>
 cudaError_t launch_sel(const FgLaunch &L) {
@@ -1226,8 +1233,8 @@ cudaError_t launch_sel(const FgLaunch &L) {
 // the per-trajectory summary is a separate instantiation so that plain F/G launches pay nothing for it
 template <int FORM, int WIND>
 cudaError_t launch_any(const FgLaunch &L) {
-    if (L.op == 1) return launch_op<FORM, WIND, MODE_JVP>(L);
-    if (L.op == 2) return launch_op<FORM, WIND, MODE_VJP>(L);
+    if (L.op == 1) return launch_sel<FORM, WIND, MODE_JVP>(L);
+    if (L.op == 2) return launch_sel<FORM, WIND, MODE_VJP>(L);
     if (L.compact) return launch_sel<FORM, WIND, MODE_COMPACT>(L);
     return L.S ? launch_sel<FORM, WIND, MODE_SUMMARY>(L) : launch_sel<FORM, WIND, MODE_PLAIN>(L);
 }
