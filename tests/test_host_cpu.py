@@ -265,3 +265,25 @@ def test_csc_pattern_is_the_column_compressed_form_of_the_reference_pattern(name
     B = sp.csc_matrix((Gc[0], ri, cp), shape=(neF, n))
     C = sp.coo_matrix((g["G"][0], (g["iGfun"], g["jGvar"])), shape=(neF, n))
     assert abs(B - C).max() == 0
+
+
+def test_new_entry_points_reject_misuse_without_touching_a_device():
+    """argument checks of the peer-buffer and matrix-free entry points come before any CUDA call; without a
+    device the allocating calls report the CUDA error and hand back NULL (never a host pointer)"""
+    import ctypes as C
+    import torch
+    L = T.load()
+    vp = C.c_void_p
+    assert L.tolcuda_jac_vec(None, 4, None, 0, None, 0, None, 0, 0) == -1
+    assert L.tolcuda_jac_tvec(None, 4, None, 0, None, 0, None, 0, 0) == -1
+    assert L.tolcuda_ipc_export(0, None, None) == -1
+    assert L.tolcuda_ipc_open(0, None, None) == -1
+    assert L.tolcuda_device_alloc(0, 1024, None) == -1
+    assert L.tolcuda_ipc_close(0, None) == 0 and L.tolcuda_device_free(0, None) == 0
+    assert L.tolcuda_enable_peer(0, 0) == 0
+    if not torch.cuda.is_available():
+        p = vp(12345)
+        rc = L.tolcuda_device_alloc(0, 1024, C.byref(p))
+        assert rc > 0 and not p.value and L.tolcuda_last_error()
+        with pytest.raises(T.TolcudaError):
+            T.PeerBuffer.alloc(0, 1024)
