@@ -241,6 +241,15 @@ int tolcuda_ipc_export(int device, const void *ptr, unsigned char handle[TOLCUDA
 int tolcuda_ipc_open(int device, const unsigned char handle[TOLCUDA_IPC_HANDLE_BYTES], void **ptr);
 int tolcuda_ipc_close(int device, void *ptr);
 int tolcuda_enable_peer(int device, int peer);
+/* Stream-ordered 32-bit flags in device memory -- the context's own device or a peer's mapping -- so that a consumer
+ * on one GPU can start on a chunk as soon as the producer's kernel for that chunk has finished on another, with no
+ * host in between:
+ *   tolcuda_stream_signal  enqueues "*flag = value" on the context's stream, after everything enqueued before it
+ *                          (the preceding kernels' stores, peer stores included, are visible before the flag is)
+ *   tolcuda_stream_wait    enqueues "wait until (int)(*flag - value) >= 0" on the context's stream
+ * flag: 4-byte aligned.  (cuStreamWriteValue32 / cuStreamWaitValue32 of the CUDA driver.) */
+int tolcuda_stream_signal(tolcuda_handle h, void *flag, unsigned int value);
+int tolcuda_stream_wait(tolcuda_handle h, const void *flag, unsigned int value);
 
 /* smallest multiple of 16 doubles (128 bytes) that holds `len` doubles */
 long tolcuda_padded_ld(long len);

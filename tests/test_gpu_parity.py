@@ -650,9 +650,10 @@ def test_peer_buffer_rows_on_one_gpu():
     B = 29
     X = _dev(T.synth.batch(g["x"][0], 4242, 0, B))
     ldF, ldG = T.evaluator.padded_ld(ev.neF), T.evaluator.padded_ld(ev.neG)
-    buf = T.PeerBuffer.alloc(0, D.peer_buffer_bytes(ev, B, staged=False))
+    buf = D.open_peer_buffer(ev, B, 0, staged=False)
     assert len(buf.handle) == T.evaluator.IPC_HANDLE_BYTES and any(buf.handle)
     buf.tensor(0, 1, B * (ldF + ldG)).fill_(float("nan"))
+    assert not buf.tensor(B * (ldF + ldG), 1, D.FLAG_BYTES // 8).any()  # the chunk flags start at zero
     F, G, kept = D.eval_and_gather_peer(ev, X, B, out=buf)
     assert kept is buf and F.shape == (B, ldF) and G.shape == (B, ldG)
     Fd = torch.empty(B, ev.neF, dtype=torch.float64, device="cuda")
@@ -683,7 +684,7 @@ def _peer_gather_worker(rank, world, port, name, B, compact, out_path):
     X = torch.from_numpy(T.synth.batch(g["x"][0], 2718, b0, b1)).cuda()
     dst = world - 1  # not rank 0: the owner is any rank
     for _ in range(2):  # a second round maps the owner's (new) buffer again
-        F, G, buf = D.eval_and_gather_peer(ev, X, B, dst=dst, compact=compact)
+        F, G, buf = D.eval_and_gather_peer(ev, X, B, dst=dst, compact=compact, chunks=3)
     if rank == dst:
         np.savez(out_path, F=F[:, :ev.neF].cpu().numpy(), G=G[:, :ev.neG].cpu().numpy())
     dist.barrier()
@@ -831,3 +832,28 @@ def test_matrix_free_products_against_the_gpu_rows_at_full_size():
     lhs, rhs = (Lam * Y).sum(1), (Z * D).sum(1)
     assert bool(((lhs - rhs).abs() <= 1e-11 * (Lam.abs() * Ya).sum(1) + 1e-13).all())
     ev.close()
+
+
+def test_stream_ordered_flags():
+    """tolcuda_stream_signal / tolcuda_stream_wait (cuStreamWriteValue32 / cuStreamWaitValue32): the flag is written
+    after the kernels enqueued before it, and a second context's stream passes a wait on a value already reached
+    (also with the counter wrapped around)"""
+    g = load_golden("S10_tempest_ts1")
+    ev, ev2 = T.Evaluator.from_golden(g), T.Evaluator.from_golden(g)
+    flag = torch.zeros(64, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    X = _dev(T.synth.batch(g["x"][0], 1, 0, 300))
+    F = torch.empty(300, ev.neF, dtype=torch.float64, device="cuda")
+    G = torch.empty(300, ev.neG, dtype=torch.float64, device="cuda")
+    for value in (1, 2, 0x7fffffff, 0x80000001):
+        ev.eval_batch_device(X, F, G, sync=False)
+        ev.stream_signal(flag.data_ptr() + 8, value)
+        ev.synchronize()
+        assert int(flag[2].item()) & 0xffffffff == value and not flag[:2].any() and not flag[3:].any()
+        ev2.stream_wait(flag.data_ptr() + 8, value)          # already reached: must not block
+        ev2.stream_wait(flag.data_ptr() + 8, value - 1)      # (int)(*flag - value) >= 0
+        ev2.eval_batch_device(X, F, G)
+    L = T.load()
+    assert L.tolcuda_stream_signal(ev.h, flag.data_ptr() + 2, 1) == -1   # misaligned
+    assert L.tolcuda_stream_wait(None, flag.data_ptr(), 1) == -1
+    ev.close(), ev2.close()

@@ -91,7 +91,7 @@ def eval_and_gather_device(ev, X, B, dst=0):
     return F, G
 
 
-def eval_and_gather_peer(ev, X, B, dst=0, out=None, compact=True):
+def eval_and_gather_peer(ev, X, B, dst=0, out=None, compact=True, chunks=4):
     """Fused evaluate + gather: rank `dst` owns one buffer holding all B rows of F and
     G; every other rank maps it over CUDA IPC (NVLink peer access) and its F/G kernel stores its shard's rows
     directly into it -- F with coalesced stores, G with the kernel's TMA bulk copies -- so the transfer happens
@@ -99,7 +99,10 @@ def eval_and_gather_peer(ev, X, B, dst=0, out=None, compact=True):
     torch.distributed only carries the 64-byte handle and the closing barrier.
       compact=True   the peers' G crosses NVLink as COMPACT rows (a third of the bytes: NVLink, at 0.9 TB/s per
                      direction, is the slower side) into a staging region of the same buffer, and `dst` expands
-                     them into rows in coordinate order at HBM speed (expand_kernel.cu)
+                     them into rows in coordinate order at HBM speed (expand_kernel.cu).  A peer's shard goes in
+                     `chunks` launches, each followed by a stream-ordered flag written into the owner's memory
+                     (tolcuda_stream_signal); the owner's stream waits on the flag (tolcuda_stream_wait) and
+                     expands that chunk while the next ones are still arriving -- no host in between
       compact=False  the peers write full rows at their final place; nothing runs on `dst` afterwards
     Returns (F [B, ldF], G [B, ldG], buffer) as CUDA tensors on rank `dst` (rows by trajectory index, padded
     leading dimensions), (None, None, None) elsewhere.  `out`: what open_peer_buffer returned on this rank, to
@@ -109,33 +112,52 @@ def eval_and_gather_peer(ev, X, B, dst=0, out=None, compact=True):
     b0, b1 = shard_range(B, r, w)
     ldF, ldG, ldC = padded_ld(ev.neF), padded_ld(ev.neG), padded_ld(ev.compact_len)
     staged = compact and w > 1
+    chunks = max(1, min(int(chunks), MAX_CHUNKS))
     nbytes = peer_buffer_bytes(ev, B, staged)
     buf = out if out is not None else open_peer_buffer(ev, B, dst, staged)
     assert buf.nbytes >= nbytes
+    buf.epoch = getattr(buf, "epoch", 0) + 1  # every rank calls in step, so the counters agree
+    assert not staged or buf.nbytes == nbytes, "the buffer was opened for another layout"
+    flags = buf.ptr + nbytes - FLAG_BYTES  # uint32 [w][MAX_CHUNKS], zeroed by open_peer_buffer
+
+    def pieces(q0, q1):
+        per = (q1 - q0 + chunks - 1) // chunks
+        return [(a, min(q1, a + per)) for a in range(q0, q1, max(per, 1))]
+
     if b1 > b0:
         assert X.shape[0] == b1 - b0
-        Fp = buf.ptr + 8 * b0 * ldF
         if staged and r != dst:
-            ev.eval_batch_ptrs(b1 - b0, X.data_ptr(), X.stride(0), Fp, ldF,
-                               buf.ptr + 8 * (B * (ldF + ldG) + b0 * ldC), ldC, compact_rows=True)
+            for ci, (a, e) in enumerate(pieces(b0, b1)):
+                ev.eval_batch_ptrs(e - a, X[a - b0:].data_ptr(), X.stride(0), buf.ptr + 8 * a * ldF, ldF,
+                                   buf.ptr + 8 * (B * (ldF + ldG) + a * ldC), ldC, compact_rows=True, sync=False)
+                ev.stream_signal(flags + 4 * (r * MAX_CHUNKS + ci), buf.epoch)
+            ev.synchronize()
         else:
-            ev.eval_batch_ptrs(b1 - b0, X.data_ptr(), X.stride(0), Fp, ldF, buf.ptr + 8 * (B * ldF + b0 * ldG), ldG)
-        # (both return after this rank's stream has drained)
+            ev.eval_batch_ptrs(b1 - b0, X.data_ptr(), X.stride(0), buf.ptr + 8 * b0 * ldF, ldF,
+                               buf.ptr + 8 * (B * ldF + b0 * ldG), ldG, sync=staged is False or w == 1)
+    F = G = None
+    if r == dst:
+        F, G = buf.tensor(0, B, ldF), buf.tensor(B * ldF, B, ldG)
+        if staged:
+            Gc = buf.tensor(B * (ldF + ldG), B, ldC)
+            for q in range(w):
+                q0, q1 = shard_range(B, q, w)
+                if q == dst or q1 <= q0:
+                    continue
+                for ci, (a, e) in enumerate(pieces(q0, q1)):
+                    ev.stream_wait(flags + 4 * (q * MAX_CHUNKS + ci), buf.epoch)
+                    ev.expand_compact_device(Gc[a:e], G[a:e], sync=False)
+            ev.synchronize()
     if w > 1:
-        dist.barrier()  # every shard has landed in the owner's memory
+        dist.barrier()  # every shard has landed (and been expanded) in the owner's memory; the staging region is free again
         if r != dst:
             if out is None:
                 buf.close()
             return None, None, None
-    F, G = buf.tensor(0, B, ldF), buf.tensor(B * ldF, B, ldG)
-    if staged:
-        Gc = buf.tensor(B * (ldF + ldG), B, ldC)
-        for q in range(w):
-            q0, q1 = shard_range(B, q, w)
-            if q != dst and q1 > q0:
-                ev.expand_compact_device(Gc[q0:q1], G[q0:q1], sync=False)
-        ev.synchronize()
     return F, G, buf
+
+
+MAX_CHUNKS = 16
 
 
 def open_peer_buffer(ev, B, dst=0, staged=True):
@@ -145,6 +167,9 @@ def open_peer_buffer(ev, B, dst=0, staged=True):
     r, w = world()
     nbytes = peer_buffer_bytes(ev, B, staged and w > 1)
     buf = PeerBuffer.alloc(ev.device, nbytes) if r == dst else None
+    if r == dst:  # the chunk flags start at zero
+        buf.tensor((nbytes - FLAG_BYTES) // 8, 1, FLAG_BYTES // 8).zero_()
+        torch.cuda.synchronize(ev.device)
     if w > 1:
         box = [buf.handle if r == dst else None]
         dist.broadcast_object_list(box, src=dst)
@@ -157,4 +182,7 @@ def peer_buffer_bytes(ev, B, staged=True):
     """bytes of the gathering rank's buffer: F rows | G rows | (staged) compact rows of the peers"""
     from .evaluator import padded_ld
     ldF, ldG, ldC = padded_ld(ev.neF), padded_ld(ev.neG), padded_ld(ev.compact_len)
-    return 8 * B * (ldF + ldG + (ldC if staged else 0))
+    return 8 * B * (ldF + ldG + (ldC if staged else 0)) + FLAG_BYTES
+
+
+FLAG_BYTES = 4096  # uint32 [world][MAX_CHUNKS] chunk flags behind the staging region (world <= 64)

@@ -325,6 +325,14 @@ class Evaluator:
             G.ctypes.data if needG else None, self.neG, S.ctypes.data, 4, flags))
         return S, F, G
 
+    def stream_signal(self, flag_ptr, value):
+        """tolcuda_stream_signal: *flag = value after everything enqueued so far on the context's stream"""
+        _l.check(self.L.tolcuda_stream_signal(self.h, C.c_void_p(flag_ptr), int(value) & 0xffffffff))
+
+    def stream_wait(self, flag_ptr, value):
+        """tolcuda_stream_wait: the context's stream waits until (int)(*flag - value) >= 0"""
+        _l.check(self.L.tolcuda_stream_wait(self.h, C.c_void_p(flag_ptr), int(value) & 0xffffffff))
+
     def set_stream(self, cuda_stream_ptr):
         """cudaStream_t as an integer (torch: stream.cuda_stream; 0 = legacy default stream)"""
         _l.check(self.L.tolcuda_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))

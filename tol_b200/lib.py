@@ -68,6 +68,8 @@ def load():
     L.tolcuda_ipc_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]
     L.tolcuda_ipc_close.argtypes = [C.c_int, vp]
     L.tolcuda_enable_peer.argtypes = [C.c_int, C.c_int]
+    L.tolcuda_stream_signal.argtypes = [vp, vp, C.c_uint]
+    L.tolcuda_stream_wait.argtypes = [vp, vp, C.c_uint]
     L.tolcuda_padded_ld.argtypes = [C.c_long]
     L.tolcuda_padded_ld.restype = C.c_long
     L.tolcuda_set_stream.argtypes = [vp, vp]

@@ -3,7 +3,8 @@ over ranks of the wall time between two barriers (kernels, transfers and the own
 
   nccl     tol_b200.dist.eval_and_gather_device: compact rows, one NCCL gather per array, expansion on the owner
   peer     tol_b200.dist.eval_and_gather_peer(compact=True): the peers' kernels store F and compact G rows straight
-           into the owner's memory over NVLink, the owner expands
+           into the owner's memory over NVLink in 4 chunks (peer1: 1, peer8: 8), each followed by a stream-ordered
+           flag the owner's stream waits on before it expands that chunk
   peerfull eval_and_gather_peer(compact=False): the peers' kernels store full rows at their final place
 
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \\
@@ -55,10 +56,10 @@ def timed(fn, reps=5):
 res = {}
 res["nccl"] = timed(lambda: D.eval_and_gather_device(ev, X, B, dst=0))
 ref = D.eval_and_gather_device(ev, X, B, dst=0)
-for label, compact in (("peer", True), ("peerfull", False)):
+for label, compact, chunks in (("peer1", True, 1), ("peer", True, 4), ("peer8", True, 8), ("peerfull", False, 1)):
     buf = D.open_peer_buffer(ev, B, 0, compact)
-    res[label] = timed(lambda: D.eval_and_gather_peer(ev, X, B, dst=0, out=buf, compact=compact))
-    F, G, _ = D.eval_and_gather_peer(ev, X, B, dst=0, out=buf, compact=compact)
+    res[label] = timed(lambda: D.eval_and_gather_peer(ev, X, B, dst=0, out=buf, compact=compact, chunks=chunks))
+    F, G, _ = D.eval_and_gather_peer(ev, X, B, dst=0, out=buf, compact=compact, chunks=chunks)
     if rank == 0:
         same = torch.equal(F[:, :ev.neF], ref[0]) and torch.equal(G[:, :ev.neG], ref[1])
         res[label + "_bitexact_vs_nccl"] = bool(same)
@@ -68,9 +69,9 @@ for label, compact in (("peer", True), ("peerfull", False)):
 if rank == 0:
     rows = 8.0 * B * (ev.neF + ev.neG)
     print("%s  B=%d on %d GPUs -> GPU 0   (rows gathered: %.2f GB)" % (name, B, w, rows / 1e9))
-    for k in ("nccl", "peer", "peerfull"):
+    for k in ("nccl", "peer1", "peer", "peer8", "peerfull"):
         print("  %-9s %8.3f ms   %6.1f GB/s of gathered rows   %.3e node-evals/s" % (
             k, res[k] * 1e3, rows / res[k] / 1e9, B * int(g["ts"]) / res[k]))
-    print("  bit-exact vs nccl path:", res.get("peer_bitexact_vs_nccl"), res.get("peerfull_bitexact_vs_nccl"))
+    print("  bit-exact vs nccl path:", [res.get(k + "_bitexact_vs_nccl") for k in ("peer1", "peer", "peer8", "peerfull")])
 ev.close()
 dist.destroy_process_group()
