@@ -290,6 +290,16 @@ def test_tolbatch_driver_end_to_end(tmp_path):
         f0 = d["trajectories"][0]["objective"]
         assert abs(f0 - g["F"][0, 0]) <= 1e-14 + 1e-12 * abs(g["F"][0, 0])
         assert outs[0]["trajectories"] == outs[1]["trajectories"]
+        # screening mode: only the summary the kernels reduce on the fly comes back; same objectives and defects
+        js = str(tmp_path / "summary.json")
+        r = subprocess.run([exe] + args + ["--root", root, "--batch", "300", "--steps", "1", "--json", js, "--summary-only"],
+                           capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stdout + r.stderr
+        sm = json.load(open(js))
+        assert sm["summary_only"] is True and sm["nonfinite"] == 0
+        for a, b in zip(sm["trajectories"], d["trajectories"]):
+            assert a["objective"] == b["objective"] and a["max_abs_defect"] == b["max_abs_defect"]
+            assert a["max_abs_boundary"] <= b["max_abs_boundary"]
 
 
 @pytest.mark.parametrize("mission,ts", [("S10", 257), ("G7", 300), ("S10", 1100), ("G7", 2049)])

@@ -10,6 +10,10 @@
 //            [--seed S] [--perturb REL,ABS] [--x-file raw_f64] [--steps K] [--json out.json]
 //            [--results DIR [--nresults K]]   the reference's snopt_results.json (src/problem.cpp:1247-1365)
 //                                             for the first K trajectories, as DIR/snopt_results_<b>.json
+//            [--summary-only]                 screening mode: only x goes to the GPUs and only the per-trajectory
+//                                             summary the kernels compute on the fly comes back
+//                                             (tolcuda_eval_batch_summary without F or G: objective, worst defect,
+//                                             worst boundary violation), no F/G rows on the host
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -28,6 +32,7 @@ struct Args {
     double enu[3] = {0, 0, 0}, goal[4] = {0, 0, 0, 0};
     std::string aircraft, mission, root = "./", xfile, json, results;
     int ts = 0, batch = 4096, gpus = 0, steps = 3, nresults = 4;
+    bool summary_only = false;
     uint64_t seed = 1;
     double rel = 0.05, abs_ = 0.01;
 };
@@ -57,7 +62,7 @@ void check(int rc, const char *what) {
 Args parse(int argc, char **argv) {
     if (argc < 10)
         die("usage: tolbatch E N U Eg Ng Ug Rg aircraft mission [--root DIR/] [--ts N] [--batch B] [--gpus G] "
-            "[--seed S] [--perturb REL,ABS] [--x-file F] [--steps K] [--json OUT]");
+            "[--seed S] [--perturb REL,ABS] [--x-file F] [--steps K] [--json OUT] [--results DIR [--nresults K]] [--summary-only]");
     Args a;
     for (int i = 0; i < 3; i++) a.enu[i] = std::atof(argv[1 + i]);  // as src/arguments.cpp:35-41 (atof)
     for (int i = 0; i < 4; i++) a.goal[i] = std::atof(argv[4 + i]);
@@ -79,6 +84,7 @@ Args parse(int argc, char **argv) {
         else if (k == "--json") a.json = val();
         else if (k == "--results") a.results = val();
         else if (k == "--nresults") a.nresults = std::atoi(val());
+        else if (k == "--summary-only") a.summary_only = true;
         else if (k == "--perturb") {
             if (std::sscanf(val(), "%lf,%lf", &a.rel, &a.abs_) != 2) die("--perturb wants REL,ABS");
         } else die("unknown option " + k);
@@ -110,10 +116,14 @@ int main(int argc, char **argv) {
     std::printf("TOLBATCH: %s / %s, ts=%d, n=%d neF=%d neG=%d, %d trajectories on %d GPU(s)\n", a.mission.c_str(),
                 a.aircraft.c_str(), ts, n, neF, neG, B, G);
 
-    double *X, *F, *Gv;
+    double *X, *F = nullptr, *Gv = nullptr, *S = nullptr;
     check(tolcuda_host_alloc(sizeof(double) * ldx * B, (void **)&X), "pinned x");
-    check(tolcuda_host_alloc(sizeof(double) * ldF * B, (void **)&F), "pinned F");
-    check(tolcuda_host_alloc(sizeof(double) * ldG * B, (void **)&Gv), "pinned G");
+    if (a.summary_only) {
+        check(tolcuda_host_alloc(sizeof(double) * 4 * B, (void **)&S), "pinned summary");
+    } else {
+        check(tolcuda_host_alloc(sizeof(double) * ldF * B, (void **)&F), "pinned F");
+        check(tolcuda_host_alloc(sizeof(double) * ldG * B, (void **)&Gv), "pinned G");
+    }
 
     // inputs: the reference's initial trajectory, perturbed per trajectory index, or a raw float64 file
     std::vector<double> x0(n);
@@ -145,7 +155,11 @@ int main(int argc, char **argv) {
             th.emplace_back([&, g]() {
                 const int per = (B + G - 1) / G, b0 = std::min(B, g * per), b1 = std::min(B, b0 + per);
                 const auto s0 = std::chrono::steady_clock::now();
-                if (b1 > b0)
+                if (b1 > b0 && a.summary_only)
+                    check(tolcuda_eval_batch_summary(h[g], b1 - b0, X + (size_t)b0 * ldx, ldx, nullptr, 0, nullptr, 0,
+                                                     S + (size_t)b0 * 4, 4, TOLCUDA_HOST_PTRS),
+                          "tolcuda_eval_batch_summary");
+                else if (b1 > b0)
                     check(tolcuda_eval_batch(h[g], b1 - b0, X + (size_t)b0 * ldx, ldx, F + (size_t)b0 * ldF, ldF,
                                              Gv + (size_t)b0 * ldG, ldG, TOLCUDA_NEED_F | TOLCUDA_NEED_G | TOLCUDA_HOST_PTRS),
                           "tolcuda_eval_batch");
@@ -154,8 +168,8 @@ int main(int argc, char **argv) {
         for (auto &t : th) t.join();
         const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         best = std::min(best, wall);
-        std::printf("TOLBATCH: step %d: %.3f ms wall, %.4g node-evals/s end to end (host x -> host F,G)\n", step,
-                    1e3 * wall, (double)B * ts / wall);
+        std::printf("TOLBATCH: step %d: %.3f ms wall, %.4g node-evals/s end to end (host x -> host %s)\n", step,
+                    1e3 * wall, (double)B * ts / wall, a.summary_only ? "summary" : "F,G");
     }
 
     // per-trajectory summary: objective, worst defect, worst boundary violation, finiteness
@@ -163,7 +177,14 @@ int main(int argc, char **argv) {
     long nonfinite = 0;
     double worst_defect = 0.0;
     std::vector<double> obj(B), defect(B), bnd(B);
-    for (int b = 0; b < B; b++) {
+    for (int b = 0; b < B && a.summary_only; b++) {
+        // what the kernels reduced on the fly: [objective, max |defect|, max boundary violation, sum defect^2]
+        const double *Sb = S + (size_t)b * 4;
+        for (int i = 0; i < 4; i++) nonfinite += !std::isfinite(Sb[i]);
+        obj[b] = Sb[0], defect[b] = Sb[1], bnd[b] = Sb[2];
+        worst_defect = std::fmax(worst_defect, Sb[1]);
+    }
+    for (int b = 0; b < B && !a.summary_only; b++) {
         const double *Fb = F + (size_t)b * ldF, *Gb = Gv + (size_t)b * ldG;
         double d = 0.0, e = 0.0;
         for (int i = 1; i < neF - nb; i++) d = std::fmax(d, std::fabs(Fb[i]));
@@ -184,6 +205,8 @@ int main(int argc, char **argv) {
                      a.mission.c_str(), a.aircraft.c_str(), ts, n, neF, neG);
         std::fprintf(f, " \"batch\": %d, \"gpus\": %d, \"best_ms\": %.6f, \"node_evals_per_s\": %.6g, \"nonfinite\": %ld,\n", B, G,
                      1e3 * best, (double)B * ts / best, nonfinite);
+        // summary-only: max_abs_boundary is the worst boundary VIOLATION (G7's dist <= dmax row counts only when exceeded)
+        std::fprintf(f, " \"summary_only\": %s,\n", a.summary_only ? "true" : "false");
         std::fprintf(f, " \"trajectories\": [\n");
         for (int b = 0; b < B; b++)
             std::fprintf(f, "  {\"b\": %d, \"objective\": %.17g, \"max_abs_defect\": %.17g, \"max_abs_boundary\": %.17g}%s\n", b,
@@ -191,6 +214,7 @@ int main(int argc, char **argv) {
         std::fprintf(f, " ]\n}\n");
         std::fclose(f);
     }
+    if (!a.results.empty() && a.summary_only) die("--results needs the F rows: not available with --summary-only");
     if (!a.results.empty())
         for (int b = 0; b < std::min(B, a.nresults); b++) {
             const std::string path = a.results + "/snopt_results_" + std::to_string(b) + ".json";
@@ -199,6 +223,6 @@ int main(int argc, char **argv) {
                   "tolcuda_write_results_json");
         }
     for (int g = 0; g < G; g++) tolcuda_destroy(h[g]);
-    tolcuda_host_free(X), tolcuda_host_free(F), tolcuda_host_free(Gv);
+    tolcuda_host_free(X), tolcuda_host_free(F), tolcuda_host_free(Gv), tolcuda_host_free(S);
     return nonfinite ? 1 : 0;
 }

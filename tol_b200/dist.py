@@ -121,8 +121,8 @@ def eval_and_gather_peer(ev, X, B, dst=0, out=None, compact=True, chunks=4):
     flags = buf.ptr + nbytes - FLAG_BYTES  # uint32 [w][MAX_CHUNKS], zeroed by open_peer_buffer
 
     def pieces(q0, q1):
-        per = (q1 - q0 + chunks - 1) // chunks
-        return [(a, min(q1, a + per)) for a in range(q0, q1, max(per, 1))]
+        per = max(1, (q1 - q0 + chunks - 1) // chunks)
+        return [(a, min(q1, a + per)) for a in range(q0, q1, per)]
 
     if b1 > b0:
         assert X.shape[0] == b1 - b0
@@ -140,13 +140,12 @@ def eval_and_gather_peer(ev, X, B, dst=0, out=None, compact=True, chunks=4):
         F, G = buf.tensor(0, B, ldF), buf.tensor(B * ldF, B, ldG)
         if staged:
             Gc = buf.tensor(B * (ldF + ldG), B, ldC)
-            for q in range(w):
-                q0, q1 = shard_range(B, q, w)
-                if q == dst or q1 <= q0:
-                    continue
-                for ci, (a, e) in enumerate(pieces(q0, q1)):
-                    ev.stream_wait(flags + 4 * (q * MAX_CHUNKS + ci), buf.epoch)
-                    ev.expand_compact_device(Gc[a:e], G[a:e], sync=False)
+            # chunk-major: the peers send concurrently, so their chunks c arrive at about the same time
+            todo = [(ci, q, a, e) for q in range(w) if q != dst
+                    for ci, (a, e) in enumerate(pieces(*shard_range(B, q, w)))]
+            for ci, q, a, e in sorted(todo):
+                ev.stream_wait(flags + 4 * (q * MAX_CHUNKS + ci), buf.epoch)
+                ev.expand_compact_device(Gc[a:e], G[a:e], sync=False)
             ev.synchronize()
     if w > 1:
         dist.barrier()  # every shard has landed (and been expanded) in the owner's memory; the staging region is free again
