@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -238,15 +239,19 @@ int tolcuda_enable_peer(int device, int peer) {
 // static runtime only)
 namespace {
 typedef int (*StreamMemOp32)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
-int stream_memop(tolcuda_ctx *h, const char *symbol, const void *flag, unsigned int value, unsigned int opflags) {
+int stream_memop(tolcuda_ctx *h, std::atomic<void *> &cached, const char *symbol, const void *flag, unsigned int value,
+                 unsigned int opflags) {
     if (!h || !flag || (reinterpret_cast<uintptr_t>(flag) & 3)) return TOLCUDA_EINVAL;
     CU(cudaSetDevice(h->cfg.device));
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    CU(cudaGetDriverEntryPoint(symbol, &fn, cudaEnableDefault, &qr));
-    if (!fn || qr != cudaDriverEntryPointSuccess) {
-        set_error(std::string(symbol) + ": not provided by this driver");
-        return TOLCUDA_EUNSUPPORTED;
+    void *fn = cached.load(std::memory_order_acquire);
+    if (!fn) {  // looked up once per process
+        cudaDriverEntryPointQueryResult qr;
+        CU(cudaGetDriverEntryPoint(symbol, &fn, cudaEnableDefault, &qr));
+        if (!fn || qr != cudaDriverEntryPointSuccess) {
+            set_error(std::string(symbol) + ": not provided by this driver");
+            return TOLCUDA_EUNSUPPORTED;
+        }
+        cached.store(fn, std::memory_order_release);
     }
     const int rc = reinterpret_cast<StreamMemOp32>(fn)(h->stream, (unsigned long long)reinterpret_cast<uintptr_t>(flag), value, opflags);
     if (rc != 0) {
@@ -258,11 +263,13 @@ int stream_memop(tolcuda_ctx *h, const char *symbol, const void *flag, unsigned 
 }  // namespace
 
 int tolcuda_stream_signal(tolcuda_handle h, void *flag, unsigned int value) {
-    return stream_memop(h, "cuStreamWriteValue32", flag, value, 0 /* CU_STREAM_WRITE_VALUE_DEFAULT: fence before the write */);
+    static std::atomic<void *> fn{nullptr};
+    return stream_memop(h, fn, "cuStreamWriteValue32", flag, value, 0 /* CU_STREAM_WRITE_VALUE_DEFAULT: fence before the write */);
 }
 
 int tolcuda_stream_wait(tolcuda_handle h, const void *flag, unsigned int value) {
-    return stream_memop(h, "cuStreamWaitValue32", flag, value, 0 /* CU_STREAM_WAIT_VALUE_GEQ */);
+    static std::atomic<void *> fn{nullptr};
+    return stream_memop(h, fn, "cuStreamWaitValue32", flag, value, 0 /* CU_STREAM_WAIT_VALUE_GEQ */);
 }
 
 int tolcuda_read_params(const char *path, double *values, int cap, int *count) {
