@@ -1206,7 +1206,8 @@ cudaError_t launch_long(const FgLaunch &L) {
     // as many warps (<= 8) as give every warp the same number of tiles, give or take one: 10 tiles -> 5 warps x 2
     const int nt = (L.c->ts + 31) / 32;
     const int rounds = (nt + LWARPS - 1) / LWARPS;
-    const int nthr = 32 * ((nt + rounds - 1) / rounds);
+    int nthr = 32 * ((nt + rounds - 1) / rounds);
+    if (L.lwarps > 0) nthr = 32 * (L.lwarps < nt ? L.lwarps : nt);  // experiments (TOLCUDA_LWARPS)
     const size_t smem = sizeof(double) * (size_t)(nthr / 32) * WARP_SMEM_B;
     static std::atomic<size_t> configured[MAX_DEVICES];  // per device, see launch_cta_as
     std::atomic<size_t> &done = configured[L.device & (MAX_DEVICES - 1)];

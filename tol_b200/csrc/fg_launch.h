@@ -24,6 +24,7 @@ struct FgLaunch {
     int op;  // 0: F/G; 1: y = J d (F receives y [neF], G holds d [n]); 2: z = J^T lambda (F holds lambda [neF], G receives z [n])
     int compact;  // G/ldG address the compact layout [R0 | 31 per window | boundary block] (host-pointer path)
     int kernel;    // 0/1 = kernel A (CTA per run of trajectories), 2 = kernel L (CTA per trajectory, tile loop; any ts)
+    int lwarps;    // kernel L: warps per CTA (0: the count that balances the tiles)
     int per;       // kernel A: trajectories per CTA (1..4)
     int per_auto;  // 1: small batches (B < 48 x SMs) use 1 regardless of `per`
     int sm_count;  // SMs of the device

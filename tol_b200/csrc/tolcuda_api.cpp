@@ -57,6 +57,7 @@ struct tolcuda_ctx {
     int kernel = 0;
     int per = 2;  // kernel A: trajectories per CTA for large batches (TOLCUDA_PER fixes it for every batch size)
     int per_auto = 1;
+    int lwarps = 0;  // kernel L: warps per CTA override (TOLCUDA_LWARPS; 0 = automatic)
     int zero_copy = 1;  // single-trajectory path: kernel works on the mapped pinned block (TOLCUDA_ZEROCOPY=0: staged copies)
     int sm_count = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -94,6 +95,7 @@ int launch(tolcuda_ctx *h, cudaStream_t st, int B, const double *x, long ldx, do
     L.needF = needF, L.needG = needG;
     L.kernel = h->kernel;
     L.per = h->per;
+    L.lwarps = h->lwarps;
     L.per_auto = h->per_auto;
     L.sm_count = h->sm_count;
     L.device = h->cfg.device;
@@ -341,6 +343,7 @@ int tolcuda_create(const tolcuda_config *cfg, tolcuda_handle *out) {
 
     if (const char *env = std::getenv("TOLCUDA_KERNEL")) h->kernel = std::atoi(env);  // tests / tuning
     if (const char *env = std::getenv("TOLCUDA_PER")) h->per = std::atoi(env), h->per_auto = 0;
+    if (const char *env = std::getenv("TOLCUDA_LWARPS")) h->lwarps = std::atoi(env);
     if (const char *env = std::getenv("TOLCUDA_ZEROCOPY")) h->zero_copy = std::atoi(env);
     if (const char *env = std::getenv("TOLCUDA_COMPACT")) h->compact_host = std::atoi(env);
 
