@@ -287,3 +287,45 @@ def test_new_entry_points_reject_misuse_without_touching_a_device():
         assert rc > 0 and not p.value and L.tolcuda_last_error()
         with pytest.raises(T.TolcudaError):
             T.PeerBuffer.alloc(0, 1024)
+
+
+def test_callback_without_a_bound_context_terminates_snopt(capfd):
+    """SURVEY.md 8b error convention: with no context bound the exported snOptA callback writes nothing into the
+    caller's arrays and sets *Status = -2 (SNOPT: terminate); the reference itself never touches Status
+    (src/DefineFG.cpp:9-48).  Host logic only -- no device is touched."""
+    import ctypes as C
+    L = T.load()
+    assert L.tolcuda_bind_global(None) == 0  # unbind whatever an earlier test left
+    n, neF, neG = T.problem_dims("S10", 3)
+    x, F, G = np.zeros(n), np.full(neF, 7.0), np.full(neG, 7.0)
+    st = C.c_int(1)  # SNOPT's first call
+    ints = [C.c_int(v) for v in (n, 1, neF, 1, neG, 0, 0, 0)]
+    dp = C.POINTER(C.c_double)
+    L.DEFINEGusrfg_(C.byref(st), C.byref(ints[0]), x.ctypes.data_as(dp), C.byref(ints[1]), C.byref(ints[2]),
+                    F.ctypes.data_as(dp), C.byref(ints[3]), C.byref(ints[4]), G.ctypes.data_as(dp), None,
+                    C.byref(ints[5]), None, C.byref(ints[6]), None, C.byref(ints[7]))
+    assert st.value == -2
+    assert (F == 7.0).all() and (G == 7.0).all() and (x == 0.0).all()
+    assert b"no context bound" in L.tolcuda_last_error()
+    assert "user function failed" in capfd.readouterr().err
+
+
+def test_tolbatch_fails_loudly_on_bad_arguments_and_without_a_device():
+    """the batch driver (counterpart of the reference CLI, src/tol.cpp:38-53): too few positional arguments,
+    an unknown option and -- on a box without a GPU -- the missing device all end with exit code 2 and a message;
+    nothing is evaluated on the CPU instead"""
+    import subprocess
+    import torch
+    exe = os.path.join(ROOT, "tol_b200", "tolbatch")
+    if not os.path.exists(exe):
+        pytest.skip("tolbatch is not built")
+    pos = ["0", "0", "70", "0", "-100", "0", "100", "tempest", "S10"]
+    r = subprocess.run([exe] + pos[:5], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage: tolbatch E N U Eg Ng Ug Rg aircraft mission" in r.stderr
+    r = subprocess.run([exe] + pos + ["--bogus", "1"], capture_output=True, text=True)
+    assert r.returncode == 2 and "unknown option --bogus" in r.stderr
+    r = subprocess.run([exe] + pos + ["--perturb", "abc"], capture_output=True, text=True)
+    assert r.returncode == 2 and "--perturb wants REL,ABS" in r.stderr
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe] + pos + ["--batch", "4"], capture_output=True, text=True)
+        assert r.returncode == 2 and "failed" in r.stderr and r.stdout == ""
