@@ -141,6 +141,21 @@ int tolcuda_problem_bounds(const tolcuda_config *cfg, double *xlow, double *xupp
 int tolcuda_write_results_json(const tolcuda_config *cfg, const char *aircraft, const char *mission, double east,
                                double north, double up, const double *x, double final_cost, const char *path);
 int tolcuda_write_results_txt(const tolcuda_config *cfg, const double *x, double final_cost, const char *path);
+
+/* The reference callback's per-call dump files (src/DefineFG.cpp:16-46, src/problem.cpp:740-756): on EVERY call the
+ * reference rewrites, in its working directory, Xoutput.txt (x, before anything is evaluated), Woutput.txt (the 12
+ * wind arrays per node, "%.6f "), Foutput.txt and Goutput.txt (one "%.14f" value per line) -- the live plotter
+ * matlab/@plotSNOPT/plotSNOPT.m:108-125 polls Xoutput.txt to draw the iterates while SNOPT runs.  They are 88 % of
+ * the reference's call time, so they are OFF by default here.  tolcuda_set_dump_dir(h, dir) (or TOLCUDA_DUMP_DIR in
+ * the environment when the context is created) makes DEFINEGusrfg_ -- and only it, as in the reference -- write the
+ * same files, byte for byte the reference's format, into `dir` ("." = where the reference puts them); NULL or ""
+ * switches them off again.  Woutput.txt is written for wind models 0 and 1.  A file that cannot be written is
+ * reported once on stderr and does not stop the solve.
+ * tolcuda_write_dump / tolcuda_write_wind_dump are the two writers on their own (host only, no CUDA): `count` values
+ * as "%.14f" lines; the wind arrays of modelWind case `wind_model` (0 or 1) along the trajectory x[1 + 11*(ts+1)]. */
+int tolcuda_set_dump_dir(tolcuda_handle h, const char *dir);
+int tolcuda_write_dump(const char *path, const double *values, long count);
+int tolcuda_write_wind_dump(const char *path, int wind_model, int ts, const double *x);
 /* the configuration a handle was created with (e.g. after tolcuda_create_from_files) */
 int tolcuda_get_config(tolcuda_handle h, tolcuda_config *cfg);
 

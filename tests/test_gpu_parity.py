@@ -61,6 +61,45 @@ def test_snopta_callback_drop_in(name):
     ev2.close()
 
 
+@pytest.mark.parametrize("name", ["S10_skywalker_ts7_gains", "G7_tempestwill_ts7_gains"])
+def test_callback_dump_files_on_request(name, tmp_path):
+    """tolcuda_set_dump_dir: DEFINEGusrfg_ rewrites the reference's per-call files (src/DefineFG.cpp:16-46) --
+    Xoutput.txt (what matlab/@plotSNOPT/plotSNOPT.m polls) and Woutput.txt equal to the files the unmodified
+    reference wrote for the same x (tests/golden/dumps), Foutput.txt / Goutput.txt the "%.14f" lines of the arrays
+    the call returned, within the parity bar of the reference's; F-only calls leave Goutput.txt alone; off again
+    after set_dump_dir(None) and by default"""
+    import os
+    from conftest import GOLDEN_DIR
+    g = load_golden(name)
+    s = 3 if name.startswith("S10") else 2
+    ref = os.path.join(GOLDEN_DIR, "dumps", "%s_s%d" % (name, s))
+    ev = T.Evaluator.from_golden(g)
+    x = g["x"][s]
+    st, F, G = ev.usrfun(x, 1, 1)
+    assert st == 0 and not list(tmp_path.iterdir())  # off by default
+    ev.set_dump_dir(tmp_path)
+    st, F, G = ev.usrfun(x, 1, 1)
+    assert st == 0
+    for f in ("Xoutput.txt", "Woutput.txt"):
+        assert (tmp_path / f).read_bytes() == open(os.path.join(ref, f), "rb").read(), f
+    for f, arr, key in (("Foutput.txt", F, "F"), ("Goutput.txt", G, "G")):
+        lines = (tmp_path / f).read_text().split("\n")
+        assert lines[-1] == "" and lines[:-1] == ["%.14f" % v for v in arr], f
+        want = np.array([float(t) for t in open(os.path.join(ref, f)).read().split()])
+        if key == "G":
+            want[g["ub_mask"]] = 0.0  # printed from uninitialised memory by the reference
+        assert np.abs(np.array([float(t) for t in lines[:-1]]) - want).max() <= 2e-14 + 1e-12 * np.abs(want).max()
+    os.remove(tmp_path / "Goutput.txt")
+    st, F, G = ev.usrfun(x, 1, 0)
+    assert st == 0 and (tmp_path / "Foutput.txt").exists() and not (tmp_path / "Goutput.txt").exists()
+    ev.set_dump_dir(None)
+    for f in ("Xoutput.txt", "Woutput.txt", "Foutput.txt"):
+        os.remove(tmp_path / f)
+    st, F, G = ev.usrfun(x, 1, 1)
+    assert st == 0 and not list(tmp_path.iterdir())
+    ev.close()
+
+
 @pytest.mark.parametrize("name", GOLDEN)
 @pytest.mark.parametrize("pad", ["dense", "padded", "odd"])
 def test_batch_device_pointers(name, pad):

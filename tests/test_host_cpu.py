@@ -329,3 +329,53 @@ def test_tolbatch_fails_loudly_on_bad_arguments_and_without_a_device():
     if not torch.cuda.is_available():
         r = subprocess.run([exe] + pos + ["--batch", "4"], capture_output=True, text=True)
         assert r.returncode == 2 and "failed" in r.stderr and r.stdout == ""
+
+
+DUMPS = sorted(os.listdir(os.path.join(GOLDEN_DIR, "dumps")))
+
+
+@pytest.mark.parametrize("case", DUMPS)
+def test_dump_files_equal_the_reference_callbacks_byte_for_byte(case, tmp_path):
+    """tolcuda_write_dump / tolcuda_write_wind_dump (what DEFINEGusrfg_ writes after tolcuda_set_dump_dir) against
+    the four files the UNMODIFIED reference callback wrote for the same state (oracle/gen_dumps_golden.py;
+    src/DefineFG.cpp:16-46, src/problem.cpp:740-756): Xoutput.txt is what matlab/@plotSNOPT/plotSNOPT.m polls.
+    F and G are the reference's own values here (the fixture's); the S10 lines that print uninitialised memory
+    (src/problemS10.cpp:397,414) are left out of the comparison."""
+    import ctypes as C
+    name, s = case.rsplit("_s", 1)
+    g = load_golden(name)
+    s = int(s)
+    L = T.load()
+    dp = C.POINTER(C.c_double)
+    ref = os.path.join(GOLDEN_DIR, "dumps", case)
+    for fname, arr in (("Xoutput.txt", g["x"][s]), ("Foutput.txt", g["F"][s]), ("Goutput.txt", g["G"][s])):
+        arr = np.ascontiguousarray(arr)
+        out = tmp_path / fname
+        assert L.tolcuda_write_dump(str(out).encode(), arr.ctypes.data_as(dp), arr.size) == 0
+        got, want = out.read_bytes().split(b"\n"), open(os.path.join(ref, fname), "rb").read().split(b"\n")
+        assert len(got) == len(want) == arr.size + 1 and got[-1] == want[-1] == b""
+        skip = set(g["ub_mask"].tolist()) if fname == "Goutput.txt" else set()
+        assert [v for i, v in enumerate(got) if i not in skip] == [v for i, v in enumerate(want) if i not in skip]
+    x = np.ascontiguousarray(g["x"][s])
+    out = tmp_path / "Woutput.txt"
+    assert L.tolcuda_write_wind_dump(str(out).encode(), int(g["wind_model"]), int(g["ts"]), x.ctypes.data_as(dp)) == 0
+    assert out.read_bytes() == open(os.path.join(ref, "Woutput.txt"), "rb").read()
+
+
+def test_dump_writers_reject_misuse(tmp_path):
+    import ctypes as C
+    L = T.load()
+    v = np.array([1.5, -0.0, 1e300, -2.5e-15])
+    dp = C.POINTER(C.c_double)
+    out = tmp_path / "v.txt"
+    assert L.tolcuda_write_dump(str(out).encode(), v.ctypes.data_as(dp), v.size) == 0
+    assert out.read_text().split("\n")[:2] == ["1.50000000000000", "-0.00000000000000"]
+    assert out.read_text().split("\n")[2] == "%.14f" % 1e300 and out.read_text().split("\n")[3] == "-0.00000000000000"
+    assert L.tolcuda_write_dump(str(out).encode(), None, 0) == 0 and out.read_bytes() == b""
+    assert L.tolcuda_write_dump(None, v.ctypes.data_as(dp), 1) == -1
+    assert L.tolcuda_write_dump(str(out).encode(), None, 3) == -1
+    assert L.tolcuda_write_dump(str(tmp_path / "no_such_dir" / "v.txt").encode(), v.ctypes.data_as(dp), 1) == -4
+    assert b"cannot open" in L.tolcuda_last_error()
+    assert L.tolcuda_write_wind_dump(str(out).encode(), 3, 2, v.ctypes.data_as(dp)) == -2  # wind cube: not written
+    assert L.tolcuda_write_wind_dump(str(out).encode(), 1, 0, v.ctypes.data_as(dp)) == -1
+    assert L.tolcuda_set_dump_dir(None, b".") == -1

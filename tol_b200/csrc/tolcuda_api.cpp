@@ -74,6 +74,8 @@ struct tolcuda_ctx {
     long launches = 0;
     double *d_grid = nullptr;  // wind cube: gx | gy | gz | v
     int *d_perm = nullptr;     // CSC position -> coordinate-order position, uploaded at first use
+    std::string dump_dir;      // DEFINEGusrfg_: the reference's per-call dump files go here (empty: none)
+    bool dump_warned = false;
 };
 
 namespace {
@@ -346,6 +348,7 @@ int tolcuda_create(const tolcuda_config *cfg, tolcuda_handle *out) {
     if (const char *env = std::getenv("TOLCUDA_LWARPS")) h->lwarps = std::atoi(env);
     if (const char *env = std::getenv("TOLCUDA_ZEROCOPY")) h->zero_copy = std::atoi(env);
     if (const char *env = std::getenv("TOLCUDA_COMPACT")) h->compact_host = std::atoi(env);
+    if (const char *env = std::getenv("TOLCUDA_DUMP_DIR")) h->dump_dir = env;
 
     int rc = 0;
     do {
@@ -807,6 +810,23 @@ int tolcuda_set_host_threads(tolcuda_handle h, int threads) {
     return 0;
 }
 
+int tolcuda_set_dump_dir(tolcuda_handle h, const char *dir) {
+    if (!h) return TOLCUDA_EINVAL;
+    h->dump_dir = dir ? dir : "";
+    h->dump_warned = false;
+    return 0;
+}
+
+int tolcuda_write_dump(const char *path, const double *values, long count) {
+    if (!path || count < 0 || (count > 0 && !values)) return TOLCUDA_EINVAL;
+    return write_value_dump(path, values, count);
+}
+
+int tolcuda_write_wind_dump(const char *path, int wind_model, int ts, const double *x) {
+    if (!path || ts < 1 || !x) return TOLCUDA_EINVAL;
+    return write_wind_dump(path, wind_model, ts, x);
+}
+
 int tolcuda_bind_global(tolcuda_handle h) {
     std::lock_guard<std::mutex> lk(g_mu);
     g_bound = h;
@@ -831,7 +851,26 @@ void DEFINEGusrfg_(int *Status, int *n, double x[], int *needF, int *neF, double
         set_error("DEFINEGusrfg_: n/neF/neG differ from the bound context's problem");
         rc = TOLCUDA_EINVAL;
     } else {
+        // the reference's dump files, in its order: X before anything is evaluated, W inside modelWind, F and G
+        // after they have been computed (src/DefineFG.cpp:16-46).  A file that cannot be written is reported once
+        // and does not stop the solve.
+        const bool dump = !h->dump_dir.empty();
+        auto dumped = [&](int e) {
+            if (e && !h->dump_warned) {
+                std::fprintf(stderr, "tolcuda: dump files: %s\n", tolcuda_last_error());
+                h->dump_warned = true;
+            }
+        };
+        const std::string dir = dump ? h->dump_dir + "/" : std::string();
+        if (dump) {
+            dumped(write_value_dump(dir + "Xoutput.txt", x, h->c.n));
+            if (h->c.wind != TOLCUDA_WIND_CUBE) dumped(write_wind_dump(dir + "Woutput.txt", h->c.wind, h->c.ts, x));
+        }
         rc = tolcuda_eval(h, x, *needF, F, *needG, G);
+        if (dump && !rc) {
+            if (*needF > 0) dumped(write_value_dump(dir + "Foutput.txt", F, h->c.neF));
+            if (*needG > 0) dumped(write_value_dump(dir + "Goutput.txt", G, h->c.neG));
+        }
     }
     if (rc) {
         std::fprintf(stderr, "tolcuda: user function failed (%d): %s\n", rc, tolcuda_last_error());

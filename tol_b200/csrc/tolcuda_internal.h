@@ -57,6 +57,10 @@ int write_results_json(const tolcuda_config &cfg, const char *aircraft, const ch
                        double north, double up, const double *x, double final_cost, const char *path);
 int write_results_txt(const tolcuda_config &cfg, const double *x, double final_cost, const char *path);
 
+// dumps.cpp: the reference callback's per-call dump files
+int write_value_dump(const std::string &path, const double *v, long count);
+int write_wind_dump(const std::string &path, int wind_model, int ts, const double *x);
+
 int read_params(const std::string &path, std::vector<double> &out);
 int read_aircraft(const std::string &root, const std::string &name, double ac[15]);
 int read_gains(const std::string &root, const std::string &mission, double gn[5]);

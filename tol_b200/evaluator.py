@@ -258,6 +258,11 @@ class Evaluator:
                              C.byref(leniu), None, C.byref(lenru))
         return st.value, F, G
 
+    def set_dump_dir(self, directory):
+        """tolcuda_set_dump_dir: the reference callback's Xoutput/Woutput/Foutput/Goutput.txt on every usrfun call
+        (src/DefineFG.cpp:16-46); None switches them off"""
+        _l.check(self.L.tolcuda_set_dump_dir(self.h, None if directory is None else str(directory).encode()))
+
     def eval_batch_host(self, X, F=None, G=None, needF=True, needG=True, full_copy=False, compact_rows=False):
         """tolcuda_eval_batch with HOST arrays (numpy, or pinned torch tensors via .numpy());
         full_copy: TOLCUDA_FULL_G_COPY; compact_rows: G receives compact rows (TOLCUDA_COMPACT_G)"""

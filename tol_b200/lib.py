@@ -78,6 +78,9 @@ def load():
     L.tolcuda_launch_count.argtypes = [vp]
     L.tolcuda_launch_count.restype = C.c_long
     L.tolcuda_bind_global.argtypes = [vp]
+    L.tolcuda_set_dump_dir.argtypes = [vp, C.c_char_p]
+    L.tolcuda_write_dump.argtypes = [C.c_char_p, dp, C.c_long]
+    L.tolcuda_write_wind_dump.argtypes = [C.c_char_p, C.c_int, C.c_int, dp]
     L.DEFINEGusrfg_.argtypes = [ip, ip, dp, ip, ip, dp, ip, ip, dp, C.c_char_p, ip, ip, ip, dp, ip]
     L.DEFINEGusrfg_.restype = None
     L.tolcuda_read_params.argtypes = [C.c_char_p, dp, C.c_int, ip]
