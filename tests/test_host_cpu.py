@@ -379,3 +379,57 @@ def test_dump_writers_reject_misuse(tmp_path):
     assert L.tolcuda_write_wind_dump(str(out).encode(), 3, 2, v.ctypes.data_as(dp)) == -2  # wind cube: not written
     assert L.tolcuda_write_wind_dump(str(out).encode(), 1, 0, v.ctypes.data_as(dp)) == -1
     assert L.tolcuda_set_dump_dir(None, b".") == -1
+
+
+def test_read_params_fuzz_against_the_reference_parser(tmp_path):
+    """tolcuda_read_params against the UNMODIFIED reference's parameters::readparams (src/parameters.cpp:14-34,
+    reached through its `gain` constructor :77-94) on generated gains.param files: every line style std::stod
+    accepts or rejects -- signs, exponents, hex floats, inf/nan, leading blanks, trailing text, CR, a literal
+    backslash-n, a single '/' as the real delimiter, out-of-range literals and denormals (skipped), comment and
+    blank lines -- five accepted values per file, as the reference's size check wants (build container only)."""
+    import shutil
+    import refclient as R
+    if not R.available():
+        pytest.skip("oracle/_ref (the compiled reference) is not present")
+    rng = np.random.default_rng(20261018)
+    accepted = ["{v!r}", "  \t{v!r}", "+{v!r}", "{v:.3e}", "{v:.17g}\\n   // gain", "{v!r}// c", "{v!r} / c", "{v!r}\r",
+                "{v!r}abc", "{v!r} 12", "{h}", "{v:.6f}/3", "{v:E}"]
+    special = ["inf", "-inf", "INFINITY", "1e308", "-1E-300", ".5", "5.", "0x1.8p3", "-0", "1e-307", "0x10", "1e+2x"]
+    rejected = ["", "   ", "// header 12", "abc 3", "/4", "e5", "1e999", "-1e999", "1e-400", "4e-320", "--3", "+-2",
+                ". 5", "\t// x", "x0x10"]
+    tmp = tmp_path / "root"
+    for d in ("aircraft", "problems"):
+        shutil.copytree(os.path.join(R.REF_PARAMS, d), tmp / d)
+    gfile = tmp / "problems" / "S10" / "gains.param"
+    os.chmod(gfile, 0o644)
+    compared = 0
+    for trial in range(60):
+        lines, count = [], 0
+        while count < 5:
+            kind = rng.integers(0, 10)
+            if kind < 5:
+                v = float(rng.standard_normal() * 10.0 ** int(rng.integers(-8, 9)))
+                lines.append(accepted[int(rng.integers(len(accepted)))].format(v=v, h=v.hex()))
+                count += 1
+            elif kind < 7:
+                lines.append(special[int(rng.integers(len(special)))])
+                count += 1
+            else:
+                lines.append(rejected[int(rng.integers(len(rejected)))])
+        for _ in range(int(rng.integers(0, 3))):
+            lines.append(rejected[int(rng.integers(len(rejected)))])
+        text = "\n".join(lines) + ("\n" if trial % 2 else "")
+        gfile.write_bytes(text.encode())
+        p = R.RefProblem.__new__(R.RefProblem)  # a problem object on the edited tree (no ts / gains rewriting)
+        p._tmp = None
+        p.h = R.lib().tolref_create(b"S10", b"tempest", 0.0, 0.0, 70.0, 0.0, -100.0, 0.0, 100.0, (str(tmp) + "/").encode())
+        got, cnt = T.read_params(gfile)
+        if not p.h:  # the reference counted something other than five values ("+-3", "- 2", ...): so must the library
+            assert cnt != 5, (text, got)
+            continue
+        want = p.params()["gn"]
+        p.close()
+        assert cnt == 5, (text, got)
+        assert np.array_equal(got.view(np.int64), want.view(np.int64)), (text, got, want)  # bit for bit, NaN included
+        compared += 1
+    assert compared >= 30
