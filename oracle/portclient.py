@@ -2,6 +2,7 @@
 reference's user-function path (oracle/fg_oracle.c).  Used by tests/, __graft_entry__.smoke() and
 bench.py's cpu_baseline / --impl reference legs only; the product package never imports it."""
 import ctypes as C
+import math
 import os
 
 import numpy as np
@@ -59,8 +60,10 @@ class PortProblem:
         form = {"G7": G7, "S10": S10}[mission]
         nb = 12 if form == G7 else 11
         if chi_d is None:
-            # reference src/problemG7.cpp:524 with xi = yi = 0 (src/problem.cpp:111-112)
-            chi_d = float(np.arctan2(goal[1] - 0.0, goal[0] - 0.0)) if form == G7 else 0.0
+            # reference src/problemG7.cpp:524 with xi = yi = 0 (src/problem.cpp:111-112).  libm's atan2 (what the
+            # reference calls), NOT numpy's: np.arctan2 is a vectorised routine of its own and differs from glibc
+            # in the last bit for ~8 % of arguments
+            chi_d = math.atan2(float(goal[1]) - 0.0, float(goal[0]) - 0.0) if form == G7 else 0.0
         self.p = ToloProblem(form, int(ts), 11, 8, nb, int(wind_model), ac[0], ac[2], ac[3], ac[4],
                              ac[5], gn[0], gn[1], gn[2], gn[4], goal[0], goal[1], goal[3], chi_d)
         self.mission, self.ts, self.nb = mission, int(ts), nb

@@ -433,3 +433,39 @@ def test_read_params_fuzz_against_the_reference_parser(tmp_path):
         assert np.array_equal(got.view(np.int64), want.view(np.int64)), (text, got, want)  # bit for bit, NaN included
         compared += 1
     assert compared >= 30
+
+
+def test_setup_fuzz_against_the_reference(tmp_path):
+    """tolcuda_problem_initial_guess / tolcuda_problem_bounds against the UNMODIFIED reference's InitialCond and
+    setLimits (src/problemG7.cpp:19-217, src/problemS10.cpp:19-219, src/problem.cpp:198-365) on random command
+    lines: both formulations, the five shipped aircraft, ts from 1 to 150, goals in every quadrant (and on the
+    axes, where atan2 and the straight-line guess have their corner cases), loiter radii from 1 m to 1 km --
+    bit for bit, together with the closed-form dimensions and pattern (build container only)."""
+    import refclient as R
+    if not R.available():
+        pytest.skip("oracle/_ref (the compiled reference) is not present")
+    rng = np.random.default_rng(20261019)
+    aircraft = ["skywalker", "tempest", "tempest_eric", "tempest_wences", "tempest_will"]
+    goals = [(400.0, 0.0), (0.0, 400.0), (-250.0, 0.0), (0.0, -90.0), (1e-3, 1e-3)]
+    for trial in range(36):
+        mission = "G7" if trial % 2 else "S10"
+        ts = int(rng.choice([1, 2, 3, 7, 31, 32, 33, 64, 100, 150]))
+        eg, ng = goals[trial % 9] if trial % 9 < len(goals) else tuple(rng.uniform(-800, 800, 2).tolist())
+        goal = (eg, ng, float(rng.uniform(-50, 120)), float(rng.choice([0.0, 1.0, 40.0, 100.0, 1000.0])))
+        enu = (float(rng.uniform(-30, 30)), float(rng.uniform(-30, 30)), float(rng.uniform(0, 150)))
+        ac = aircraft[trial % 5]
+        p = R.RefProblem(mission, ac, enu, goal, ts=ts)
+        prm = p.params()
+        lm = prm["lm"]
+        cfg = T.make_config(mission, ts, prm["ac"], prm["gn"], prm["goal"],
+                            limits=[lm[0], lm[1], lm[5], lm[2], lm[6], lm[3], lm[7], lm[4]], solver_tol=prm["sn"][4:6])
+        what = (mission, ac, ts, enu, goal)
+        assert T.problem_dims(mission, ts) == (p.n, p.neF, p.neG), what
+        i, j = T.problem_pattern(mission, ts)
+        ri, rj = p.pattern()
+        assert np.array_equal(i, ri) and np.array_equal(j, rj), what
+        x0, rx0 = T.initial_guess(cfg), p.x0()
+        assert np.array_equal(x0.view(np.int64), rx0.view(np.int64)), (what, np.abs(x0 - rx0).max())
+        for got, want, key in zip(T.bounds(cfg), p.bounds(), ("xlow", "xupp", "Flow", "Fupp")):
+            assert np.array_equal(got.view(np.int64), want.view(np.int64)), (what, key)
+        p.close()
