@@ -469,3 +469,42 @@ def test_setup_fuzz_against_the_reference(tmp_path):
         for got, want, key in zip(T.bounds(cfg), p.bounds(), ("xlow", "xupp", "Flow", "Fupp")):
             assert np.array_equal(got.view(np.int64), want.view(np.int64)), (what, key)
         p.close()
+
+
+def test_result_files_fuzz_against_the_reference(tmp_path):
+    """tolcuda_write_results_json / _txt against the UNMODIFIED reference's writeJSON / writeTXT
+    (src/problem.cpp:1247-1418, jsoncpp's StyledWriter) on random states salted with the values number
+    formatting trips over: +-0, integers, powers of ten, 0.1-like decimals, huge and tiny magnitudes,
+    denormals (build container only)"""
+    import refclient as R
+    if not R.available():
+        pytest.skip("oracle/_ref (the compiled reference) is not present")
+    rng = np.random.default_rng(20261022)
+    salt = np.array([0.0, -0.0, 1.0, -1.0, 10.0, 100.0, 1e5, 1e15, 1e16, 1e17, 1e21, 1e22, -1e-5, 1e-4, 0.1, 0.2, 0.3,
+                     1.0 / 3.0, 2.5, 123456789.0, 1e-300, 5e-324, 1.7976931348623157e308, 4.35, 0.5, 1e-7, 123.456,
+                     9007199254740993.0, 1e-10, 99999.99999999999])
+    aircraft = ["skywalker", "tempest", "tempest_eric", "tempest_wences", "tempest_will"]
+    for trial in range(24):
+        mission = "G7" if trial % 2 else "S10"
+        ts = int(rng.choice([1, 2, 3, 9, 40]))
+        ac = aircraft[trial % 5]
+        enu = tuple(float(v) for v in rng.choice([0.0, 70.0, -3.5, 12.25], 3))
+        goal = tuple(float(v) for v in rng.uniform(-300, 300, 3)) + (float(rng.choice([0.0, 100.0, 33.3])),)
+        p = R.RefProblem(mission, ac, enu, goal, ts=ts)
+        prm = p.params()
+        lm = prm["lm"]
+        cfg = T.make_config(mission, ts, prm["ac"], prm["gn"], prm["goal"],
+                            limits=[lm[0], lm[1], lm[5], lm[2], lm[6], lm[3], lm[7], lm[4]], solver_tol=prm["sn"][4:6])
+        x = p.x0() * (1 + 0.3 * rng.uniform(-1, 1, p.n))
+        k = rng.uniform(0, 1, p.n) < 0.4
+        x[k] = rng.choice(salt, int(k.sum())) * rng.choice([1.0, -1.0], int(k.sum()))
+        F0 = float(rng.choice(salt)) if trial % 3 else float(rng.standard_normal() * 1e3)
+        d = tmp_path / ("t%d" % trial)
+        d.mkdir()
+        p.write_json(x, F0, d / "ref.json")
+        ref_txt = p.write_txt(x, F0, str(d))
+        p.close()
+        T.write_results_json(cfg, ac, mission, enu, x, F0, d / "ours.json")
+        T.write_results_txt(cfg, x, F0, d / "ours.txt")
+        assert (d / "ours.json").read_bytes() == (d / "ref.json").read_bytes(), (trial, mission, ts)
+        assert (d / "ours.txt").read_bytes() == open(ref_txt, "rb").read(), (trial, mission, ts)
