@@ -89,6 +89,14 @@ int tolcuda_create_from_files(const char *root, const char *aircraft, const char
                               double east, double north, double up, double east_goal,
                               double north_goal, double up_goal, double radius_goal,
                               int ts_override, int device, tolcuda_handle *out);
+/* The first half of tolcuda_create_from_files on its own (host only, no CUDA): the reference's files and command
+ * line as a tolcuda_config -- what the reference's `aircraft`, `gain`, `limit`, `snopt` constructors and
+ * problem::problem hold afterwards (src/parameters.cpp:42-148, src/problem.cpp:13-60: ENU -> NED goal, degrees ->
+ * radians); wind model 1, the one the reference falls back to (src/problem.cpp:77). */
+int tolcuda_config_from_files(const char *root, const char *aircraft, const char *mission,
+                              double east, double north, double up, double east_goal,
+                              double north_goal, double up_goal, double radius_goal,
+                              int ts_override, int device, tolcuda_config *out);
 
 /* Wind model 3 of the reference: the wind cube that reference cacheWind pulls from its MongoDB server
  * (src/problem.cpp:371-460: cache[i][j][k], i < ne, j < nn, k < nu) is handed over by the caller and kept in

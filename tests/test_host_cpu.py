@@ -508,3 +508,41 @@ def test_result_files_fuzz_against_the_reference(tmp_path):
         T.write_results_txt(cfg, x, F0, d / "ours.txt")
         assert (d / "ours.json").read_bytes() == (d / "ref.json").read_bytes(), (trial, mission, ts)
         assert (d / "ours.txt").read_bytes() == open(ref_txt, "rb").read(), (trial, mission, ts)
+
+
+def test_config_from_files_equals_what_the_reference_holds(tmp_path):
+    """tolcuda_config_from_files (the file-reading half of tolcuda_create_from_files, host only) against the
+    members of the UNMODIFIED reference's problem object built from the same files and command line
+    (src/parameters.cpp:42-148, src/problem.cpp:13-60): aircraft with its degree -> radian conversions, gains,
+    limits, solver tolerances, ts, the ENU -> NED goal; and the errors of the reference's own checks"""
+    import refclient as R
+    if not R.available():
+        pytest.skip("oracle/_ref (the compiled reference) is not present")
+    root = R.REF_PARAMS + "/"
+    rng = np.random.default_rng(5)
+    for trial, ac in enumerate(["skywalker", "tempest", "tempest_eric", "tempest_wences", "tempest_will"] * 2):
+        mission = "G7" if trial % 2 else "S10"
+        enu = tuple(float(v) for v in rng.uniform(-50, 150, 3))
+        goal = tuple(float(v) for v in rng.uniform(-400, 400, 4))
+        p = R.RefProblem(mission, ac, enu, goal)
+        prm = p.params()
+        cfg = T.config_from_files(root, ac, mission, enu, goal)
+        assert (cfg.formulation, cfg.ts, cfg.wind_model) == ({"G7": 7, "S10": 10}[mission], p.ts, prm["wind_model"])
+        assert list(cfg.aircraft) == prm["ac"].tolist()
+        assert list(cfg.gains) == prm["gn"].tolist()
+        lm = prm["lm"]  # member order dtmin,dtmax,xmax,ymax,zmax,xmin,ymin,zmin -> file order
+        assert list(cfg.limits) == [lm[0], lm[1], lm[5], lm[2], lm[6], lm[3], lm[7], lm[4]]
+        assert list(cfg.solver_tol) == prm["sn"][4:6].tolist()
+        assert np.array_equal(np.array(list(cfg.goal)).view(np.int64), prm["goal"].view(np.int64))  # -0.0 included
+        # and the setup built from it is the reference's
+        assert np.array_equal(T.initial_guess(cfg), p.x0())
+        for got, want in zip(T.bounds(cfg), p.bounds()):
+            assert np.array_equal(got, want)
+        p.close()
+    assert T.config_from_files(root, "tempest", "S10", ts=37).ts == 37
+    with pytest.raises(T.TolcudaError, match="not recognized"):
+        T.config_from_files(root, "tempest", "S11")
+    with pytest.raises(T.TolcudaError, match="cannot open parameter file"):
+        T.config_from_files(root, "no_such_aircraft", "S10")
+    with pytest.raises(T.TolcudaError, match="cannot open parameter file"):
+        T.config_from_files(str(tmp_path) + "/", "tempest", "S10")

@@ -378,10 +378,10 @@ int tolcuda_create(const tolcuda_config *cfg, tolcuda_handle *out) {
     return 0;
 }
 
-int tolcuda_create_from_files(const char *root, const char *aircraft, const char *mission,
+int tolcuda_config_from_files(const char *root, const char *aircraft, const char *mission,
                               double east, double north, double up, double east_goal,
                               double north_goal, double up_goal, double radius_goal,
-                              int ts_override, int device, tolcuda_handle *out) {
+                              int ts_override, int device, tolcuda_config *out) {
     (void)east, (void)north, (void)up;  // stored by the reference, unused on the evaluation path
     if (!root || !aircraft || !mission || !out) return TOLCUDA_EINVAL;
     tolcuda_config cfg;
@@ -414,6 +414,20 @@ int tolcuda_create_from_files(const char *root, const char *aircraft, const char
     cfg.goal[1] = east_goal;
     cfg.goal[2] = -up_goal;
     cfg.goal[3] = radius_goal;
+    *out = cfg;
+    return 0;
+}
+
+int tolcuda_create_from_files(const char *root, const char *aircraft, const char *mission,
+                              double east, double north, double up, double east_goal,
+                              double north_goal, double up_goal, double radius_goal,
+                              int ts_override, int device, tolcuda_handle *out) {
+    if (!out) return TOLCUDA_EINVAL;
+    *out = nullptr;
+    tolcuda_config cfg;
+    int e = tolcuda_config_from_files(root, aircraft, mission, east, north, up, east_goal, north_goal, up_goal,
+                                      radius_goal, ts_override, device, &cfg);
+    if (e) return e;
     return tolcuda_create(&cfg, out);
 }
 

@@ -61,6 +61,15 @@ def make_config(mission, ts, aircraft, gains, goal_ned, wind_model=1, device=0, 
     return cfg
 
 
+def config_from_files(root, aircraft, mission, enu=(0.0, 0.0, 0.0), goal_enu=(0.0, 0.0, 0.0, 0.0), ts=0, device=0):
+    """tolcuda_config_from_files: the reference's .param files and command line as a Config (host only)"""
+    cfg = _l.Config()
+    _l.check(_l.load().tolcuda_config_from_files(str(root).encode(), aircraft.encode(), mission.encode(),
+                                                 *[float(v) for v in enu], *[float(v) for v in goal_enu],
+                                                 int(ts), int(device), C.byref(cfg)))
+    return cfg
+
+
 def initial_guess(cfg):
     """reference InitialCond: x0[n] (host only)"""
     n, _, _ = problem_dims(cfg.formulation, cfg.ts)

@@ -35,6 +35,8 @@ def load():
     L.tolcuda_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
     L.tolcuda_create_from_files.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p] + [C.c_double] * 7 + \
         [C.c_int, C.c_int, C.POINTER(vp)]
+    L.tolcuda_config_from_files.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p] + [C.c_double] * 7 + \
+        [C.c_int, C.c_int, C.POINTER(Config)]
     L.tolcuda_destroy.argtypes = [vp]
     L.tolcuda_set_wind_grid.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp]
     L.tolcuda_dims.argtypes = [vp, ip, ip, ip]
