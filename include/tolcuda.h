@@ -51,6 +51,18 @@ extern "C" {
 #define TOLCUDA_FULL_G_COPY 0x100 /* host pointers only: copy full G rows across PCIe instead of
                                      compact rows expanded by host threads (see tolcuda_eval_batch) */
 
+/* Device pointers + TOLCUDA_NO_SYNC only: this launch may START while the kernel enqueued immediately before it on
+ * the stream is still finishing (programmatic dependent launch): its CTAs move into the SMs the previous grid's
+ * tail has left.  The caller guarantees that x was not written by that preceding kernel (x is read early).
+ *   TOLCUDA_OVERLAP           the kernel waits for the preceding kernel to complete before its first store, so
+ *                             F/G/summary may alias whatever that kernel read or wrote (e.g. the same F/G again)
+ *   TOLCUDA_OVERLAP_DISJOINT  no wait at all: the caller also guarantees that F/G/summary overlap nothing the
+ *                             preceding kernel reads or writes (e.g. consecutive chunks of a batch, or two sets
+ *                             of result buffers used alternately) */
+#define TOLCUDA_OVERLAP 0x200
+#define TOLCUDA_OVERLAP_DISJOINT 0x400
+#define TOLCUDA_FLAGS_ALL 0x7f3 /* every bit defined above; others are rejected with TOLCUDA_EINVAL */
+
 typedef struct tolcuda_ctx *tolcuda_handle;
 
 /* What reference `problem::problem(arguments&)` gathers before the first callback
@@ -78,7 +90,8 @@ typedef struct tolcuda_config {
 
 /* Replaces the problemG7 / problemS10 construction in reference src/tol.cpp:5-36 for the
  * evaluation path: builds the sparsity pattern once (closed form of countG, src/problem.cpp:813-919),
- * uploads the constants to __constant__ memory, creates the stream and pinned staging buffers. */
+ * builds the kernels' constants (handed to every launch as a __grid_constant__ parameter: constant bank, immediate
+ * operands), creates the stream and pinned staging buffers. */
 int tolcuda_create(const tolcuda_config *cfg, tolcuda_handle *out);
 
 /* Same, reading the reference's own files: <root>aircraft/<aircraft>.param,
@@ -180,7 +193,7 @@ int tolcuda_eval(tolcuda_handle h, const double *x, int needF, double *F, int ne
  * tabG, src/problem.cpp:1038,1084,1098,1112,1170,1182,1204) and two equal -dt, so by default only the
  * x-dependent values cross PCIe (compact rows) and a pool of host threads places them in the caller's G
  * and writes the constants as literals; the rows the caller sees are bit for bit those of the
- * device-pointer path.  TOLCUDA_FULL_G_COPY (or environment TOLCUDA_COMPACT=0) copies full rows instead. */
+ * device-pointer path.  TOLCUDA_FULL_G_COPY (or tolcuda_set_option(h, "compact_host", 0)) copies full rows instead. */
 int tolcuda_eval_batch(tolcuda_handle h, int B, const double *x, long ldx, double *F, long ldF,
                        double *G, long ldG, int flags);
 
@@ -225,6 +238,23 @@ int tolcuda_jac_tvec(tolcuda_handle h, int B, const double *x, long ldx, const d
 /* host threads the host-pointer batch path of this context expands compact rows with (0 = default:
  * environment TOLCUDA_HOST_THREADS, else the cores available to the process / LOCAL_WORLD_SIZE) */
 int tolcuda_set_host_threads(tolcuda_handle h, int threads);
+
+/* Execution-strategy options of a context.  EVERY value of EVERY option yields the same bits in F and G (tested);
+ * they choose between equivalent ways of running the same arithmetic:
+ *   "kernel"         0 (default): one CTA per run of trajectories for ts <= 256, the tile-loop kernel beyond;
+ *                    2: the tile-loop kernel for any ts
+ *   "per"            trajectories per CTA, 1..4; 0 (default) = 2 for large batches, 1 below "per_min_waves" waves
+ *   "per_min_waves"  waves of single-trajectory CTAs; -1 (default) = 24, 8 for TOLCUDA_OVERLAP_DISJOINT launches
+ *   "tail_x4"        quarter-waves of single-trajectory CTAs a grid of runs ends on; -1 (default) = 2, and 0 for
+ *                    TOLCUDA_OVERLAP_DISJOINT launches (the next grid fills the tail)
+ *   "lwarps"         warps per CTA of the tile-loop kernel, 1..8; 0 (default) = the count that balances the tiles
+ *   "zero_copy"      1 (default): the single-trajectory path lets the kernel read x / write F, G in mapped pinned
+ *                    host memory; 0: staged cudaMemcpyAsync copies
+ *   "compact_host"   1 (default): the host-pointer batch path moves compact G rows across PCIe and expands them on
+ *                    host threads; 0: full rows cross PCIe (as with TOLCUDA_FULL_G_COPY)
+ *   "chunk_mb"       host-pointer batch path: device megabytes per pipeline lane (default 32)
+ * Returns TOLCUDA_EINVAL for an unknown name or a value out of range. */
+int tolcuda_set_option(tolcuda_handle h, const char *name, long value);
 
 /* Same evaluation plus a per-trajectory summary computed inside the kernel from values it already holds
  * (a device-side consumer of F; nothing of the kind exists in the reference, where SNOPT alone reads F):

@@ -131,8 +131,7 @@ def test_batch_host_pointers_chunked(name, monkeypatch):
     X = T.synth.batch(x0, 555, 0, B)
     Fr, Gr = np.empty((B, p.neF)), np.empty((B, p.neG))
     p.eval_many(X, Fr, Gr)
-    monkeypatch.setenv("TOLCUDA_CHUNK_MB", "1")
-    ev = T.Evaluator.from_golden(g)
+    ev = T.Evaluator.from_golden(g, options={"chunk_mb": 1})
     F, G = ev.eval_batch_host(X)
     assert_parity(F, Fr, name + " host F")
     assert_parity(G, Gr, name + " host G")
@@ -152,11 +151,9 @@ def test_compact_rows_path_equals_full_rows(name, kernel, monkeypatch):
     on host threads.  Its rows must be BIT-IDENTICAL to full rows copied from the device (TOLCUDA_FULL_G_COPY),
     for aligned and 8-byte-shifted destinations, through several chunks and lanes; compact rows requested
     by the caller (TOLCUDA_COMPACT_G, host and device pointers) expand to the same rows too."""
-    monkeypatch.setenv("TOLCUDA_KERNEL", str(kernel))
-    monkeypatch.setenv("TOLCUDA_CHUNK_MB", "1")
     g = load_golden(name)
     m, ts = str(g["mission"]), int(g["ts"])
-    ev = T.Evaluator.from_golden(g)
+    ev = T.Evaluator.from_golden(g, options={"kernel": kernel, "chunk_mb": 1})
     B = 101
     X = T.synth.batch(g["x"][0], 4242, 0, B)
     Ff, Gf = ev.eval_batch_host(X, full_copy=True)
@@ -198,14 +195,13 @@ def test_section_8d_batches_against_oracle(name, seed0, kernel, monkeypatch, ora
     """configs 3 and 4 of BASELINE.json on a 64-trajectory subset, through both kernels (CTA per
     run of trajectories / CTA per trajectory with a tile loop); the lane-copy fallback of the TMA bulk
     stores is exercised by the odd-leading-dimension cases of test_batch_device_pointers"""
-    monkeypatch.setenv("TOLCUDA_KERNEL", str(kernel))
     g = load_golden(name)
     p = port_from_golden(g)
     B = 64
     X = T.synth.batch(g["x"][0], seed0, 1000, 1000 + B)
     Fr, Gr = np.empty((B, p.neF)), np.empty((B, p.neG))
     p.eval_many(X, Fr, Gr)
-    ev = T.Evaluator.from_golden(g)
+    ev = T.Evaluator.from_golden(g, options={"kernel": kernel})
     Xd = _dev(X)
     F = torch.empty(B, p.neF, dtype=torch.float64, device="cuda")
     G = torch.empty(B, p.neG, dtype=torch.float64, device="cuda")
@@ -410,9 +406,8 @@ def test_fused_trajectory_summary(name, kernel, monkeypatch):
     """tolcuda_eval_batch_summary: objective / max|defect| / max boundary violation / sum defect^2 computed
     in the kernel equal the same quantities computed on the host from the kernel's own F (max: exactly;
     sum of squares: to rounding), with and without F/G being written"""
-    monkeypatch.setenv("TOLCUDA_KERNEL", str(kernel))
     g = load_golden(name)
-    ev = T.Evaluator.from_golden(g)
+    ev = T.Evaluator.from_golden(g, options={"kernel": kernel})
     B = 33
     X = T.synth.batch(g["x"][0], 909, 0, B)
     S, F, G = ev.summary_host(X, needF=True, needG=True)
@@ -539,12 +534,69 @@ def test_runs_of_trajectories_per_cta(name, per, monkeypatch):
     ev = T.Evaluator.from_golden(g)
     Fd, Gd = ev.eval_batch_host(X, full_copy=True)
     ev.close()
-    monkeypatch.setenv("TOLCUDA_PER", str(per))
-    ev = T.Evaluator.from_golden(g)
+    ev = T.Evaluator.from_golden(g, options={"per": per})
     for B in (23, 22, 1):
         F, G = ev.eval_batch_host(X[:B], full_copy=True)
         assert np.array_equal(F.view(np.int64), Fd[:B].view(np.int64))
         assert np.array_equal(G.view(np.int64), Gd[:B].view(np.int64))
+    ev.close()
+
+
+@pytest.mark.parametrize("name", ["S10_tempest_ts200", "G7_skywalker_ts100", "S10_tempesteric_ts33", "G7_tempestwences_ts45_gains"])
+def test_launch_shapes_and_overlapped_launches_give_the_same_bits(name):
+    """Every launch shape (trajectories per CTA, single-trajectory tail of the grid) and both forms of programmatic
+    dependent launch (TOLCUDA_OVERLAP: the next launch starts during the previous one's tail and waits before its
+    first store; TOLCUDA_OVERLAP_DISJOINT: no wait, alternating result buffers) must reproduce the bits of plain,
+    serialised launches -- including when consecutive overlapped launches write DIFFERENT values into the same
+    buffers (the wait is what makes that legal)."""
+    g = load_golden(name)
+    B = 1500  # several waves of CTAs on 148 SMs, an odd run count, a ragged end
+    ev = T.Evaluator.from_golden(g)
+    ldx, ldF, ldG = (T.evaluator.padded_ld(v) for v in (ev.n, ev.neF, ev.neG))
+    Xs = []
+    for q in range(3):
+        X = np.zeros((B, ldx))
+        T.synth.batch(g["x"][0], 31000 + 7 * q, 0, B, out=X)
+        Xs.append(_dev(X))
+    ref = []
+    for X in Xs:
+        F = torch.full((B, ldF), float("nan"), dtype=torch.float64, device="cuda")
+        G = torch.full((B, ldG), float("nan"), dtype=torch.float64, device="cuda")
+        ev.eval_batch_device(X, F, G)
+        ref.append((F.cpu().numpy().view(np.int64), G.cpu().numpy().view(np.int64)))
+    shapes = [(1, 0), (2, 0), (2, 1), (2, 4), (2, 64), (3, 2), (4, 3)]
+    for per, tail in shapes:
+        ev.set_option("per", per)
+        ev.set_option("tail_x4", tail)
+        for nb in (B, B - 1, 3, 1):
+            F = torch.full((B, ldF), float("nan"), dtype=torch.float64, device="cuda")
+            G = torch.full((B, ldG), float("nan"), dtype=torch.float64, device="cuda")
+            ev.eval_batch_device(Xs[0][:nb], F[:nb], G[:nb])
+            assert np.array_equal(F.cpu().numpy().view(np.int64)[:nb], ref[0][0][:nb]), (per, tail, nb)
+            assert np.array_equal(G.cpu().numpy().view(np.int64)[:nb], ref[0][1][:nb]), (per, tail, nb)
+            assert torch.isnan(F[nb:]).all() and torch.isnan(G[nb:]).all()
+    ev.set_option("per", 0)
+    ev.set_option("tail_x4", -1)
+    nF, nG = ev.neF, ev.neG
+    # overlap = 1: twelve launches back to back into the SAME buffers, inputs cycling; the last one's values must stand
+    F = torch.empty(B, ldF, dtype=torch.float64, device="cuda")
+    G = torch.empty(B, ldG, dtype=torch.float64, device="cuda")
+    for rep in range(3):
+        for i in range(12):
+            ev.eval_batch_device(Xs[i % 3], F, G, sync=False, overlap=1)
+        last = 11 % 3
+        ev.synchronize()
+        assert np.array_equal(F.cpu().numpy().view(np.int64)[:, :nF], ref[last][0][:, :nF])
+        assert np.array_equal(G.cpu().numpy().view(np.int64)[:, :nG], ref[last][1][:, :nG])
+    # overlap = 2: consecutive launches write different buffers and may run concurrently
+    outs = [(torch.empty(B, ldF, dtype=torch.float64, device="cuda"), torch.empty(B, ldG, dtype=torch.float64, device="cuda"))
+            for _ in range(3)]
+    for i in range(12):
+        ev.eval_batch_device(Xs[i % 3], outs[i % 3][0], outs[i % 3][1], sync=False, overlap=2)
+    ev.synchronize()
+    for q in range(3):
+        assert np.array_equal(outs[q][0].cpu().numpy().view(np.int64)[:, :nF], ref[q][0][:, :nF])
+        assert np.array_equal(outs[q][1].cpu().numpy().view(np.int64)[:, :nG], ref[q][1][:, :nG])
     ev.close()
 
 
@@ -574,6 +626,19 @@ def test_api_misuse_is_reported_not_executed():
     assert L.tolcuda_eval_batch_summary(ev.h, 1, x.ctypes.data, ev.n, F.ctypes.data, ev.neF, G.ctypes.data, ev.neG,
                                         S.ctypes.data, 4, flags | T.evaluator.COMPACT_G) == -2     # EUNSUPPORTED
     assert np.isnan(F).all() and np.isnan(G).all()
+    # the release library has no experiment switches: flag bits it does not define are rejected, nothing runs
+    l0 = ev.launches
+    for bad in (0x10000, 0x20000 | flags, 0x800 | flags, 1 << 30):
+        assert L.tolcuda_eval_batch(ev.h, 1, x.ctypes.data, ev.n, F.ctypes.data, ev.neF, G.ctypes.data, ev.neG, bad | flags) == -1
+        assert b"unknown flag" in L.tolcuda_last_error()
+    # TOLCUDA_OVERLAP is a device-pointer, no-sync option
+    assert L.tolcuda_eval_batch(ev.h, 1, x.ctypes.data, ev.n, F.ctypes.data, ev.neF, G.ctypes.data, ev.neG,
+                                flags | T.evaluator.OVERLAP) == -1
+    assert ev.launches == l0 and np.isnan(F).all() and np.isnan(G).all()
+    # options: unknown names and values out of range are refused and change nothing
+    assert L.tolcuda_set_option(ev.h, b"no_such_option", 1) == -1
+    assert L.tolcuda_set_option(ev.h, b"per", 5) == -1 and L.tolcuda_set_option(ev.h, b"kernel", 3) == -1
+    assert L.tolcuda_set_option(None, b"per", 1) == -1
     # unsupported configurations never reach the device
     cfg = T.make_config("S10", 100, g["ac"], g["gn"], g["goal_ned"])
     h = C.c_void_p()
@@ -817,10 +882,9 @@ def test_matrix_free_jacobian_products(name, kernel, monkeypatch, oracle_built):
     adjoint identity lambda.(J d) == (J^T lambda).d"""
     if name not in GOLDEN:
         pytest.skip("fixture not present")
-    monkeypatch.setenv("TOLCUDA_KERNEL", str(kernel))
     g = load_golden(name)
     p = port_from_golden(g)
-    ev = T.Evaluator.from_golden(g)
+    ev = T.Evaluator.from_golden(g, options={"kernel": kernel})
     iG, jG = ev.pattern()
     B = 21
     rng = np.random.default_rng(77)

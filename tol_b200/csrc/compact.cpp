@@ -44,14 +44,7 @@ struct RecMap {
 };
 constexpr RecMap make_map() {
     RecMap r{};
-    for (int j = 0; j < REC; j++) r.m[j] = -1;
-    // same positions as record_store / record_init in fg_kernels.cu
-    constexpr int pos[NVAR] = {0,  4,  5,  6,  13, 17, 18, 19, 26, 30, 31, 39, 43, 44, 45, 47,
-                               50, 52, 56, 57, 58, 59, 60, 65, 69, 70, 71, 72, 73, 78, 91};
-    for (int i = 0; i < NVAR; i++) r.m[pos[i]] = (int8_t)i;
-    r.m[1] = r.m[15] = r.m[29] = r.m[85] = r.m[99] = -3;
-    for (int s = 0; s < TOLCUDA_PF; s++) r.m[13 * s + 12] = -2;
-    r.m[87] = r.m[101] = -4;
+    for (int j = 0; j < REC; j++) r.m[j] = (int8_t)tolcuda_rec_kind(j);  // the one table, fg_const.h
     return r;
 }
 constexpr RecMap kMap = make_map();

@@ -17,19 +17,13 @@ constexpr int WPB = 64;      // windows per block
 constexpr int THREADS = 208; // the pairs of a 4-record group: 4 * 104 / 2
 
 // record position -> source: >= 0 index into the window's 31 values, -1: 0.0, -2: +1.0, -3: -1.0, -4: -dt
-// (same table as compact.cpp / record_store in fg_kernels.cu)
+// (tolcuda_rec_kind, fg_const.h)
 struct RecMap {
     signed char m[REC];
 };
 constexpr RecMap make_map() {
     RecMap r{};
-    for (int j = 0; j < REC; j++) r.m[j] = -1;
-    constexpr int pos[NVAR] = {0,  4,  5,  6,  13, 17, 18, 19, 26, 30, 31, 39, 43, 44, 45, 47,
-                               50, 52, 56, 57, 58, 59, 60, 65, 69, 70, 71, 72, 73, 78, 91};
-    for (int i = 0; i < NVAR; i++) r.m[pos[i]] = (signed char)i;
-    r.m[1] = r.m[15] = r.m[29] = r.m[85] = r.m[99] = -3;
-    for (int s = 0; s < TOLCUDA_PF; s++) r.m[13 * s + 12] = -2;
-    r.m[87] = r.m[101] = -4;
+    for (int j = 0; j < REC; j++) r.m[j] = (signed char)tolcuda_rec_kind(j);
     return r;
 }
 __constant__ RecMap c_map = make_map();

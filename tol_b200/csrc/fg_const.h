@@ -15,6 +15,29 @@
 #define TOLCUDA_REC 104    /* G values per collocation window: 8 defect rows x 13 columns */
 #define TOLCUDA_NVAR 31    /* of which depend on x (two more are -dt, the rest 0 or +-1) */
 
+#ifdef __CUDACC__
+#define TOLCUDA_HD __host__ __device__
+#else
+#define TOLCUDA_HD
+#endif
+
+// THE table of a window's Jacobian record (row s = p / 13 of the 8 defect rows, column j = p % 13: 0 = dt,
+// 1..11 = component j-1 of node k, 12 = component s of node k+1; reference src/problem.cpp:1074-1192, 1204).
+// What record position p holds: >= 0: index into the window's TOLCUDA_NVAR x-dependent values, in coordinate
+// order; -1: 0.0; -2: +1.0; -3: -1.0; -4: -dt.  Every user -- the kernels' record slots (fg_kernels.cu), the
+// host expansion of compact rows (compact.cpp) and the device expansion (expand_kernel.cu) -- derives its
+// layout from this one function.
+TOLCUDA_HD constexpr int tolcuda_rec_kind(int p) {
+    constexpr int pos[TOLCUDA_NVAR] = {0,  4,  5,  6,  13, 17, 18, 19, 26, 30, 31, 39, 43, 44, 45, 47,
+                                       50, 52, 56, 57, 58, 59, 60, 65, 69, 70, 71, 72, 73, 78, 91};
+    for (int i = 0; i < TOLCUDA_NVAR; i++)
+        if (pos[i] == p) return i;
+    if (p == 1 || p == 15 || p == 29 || p == 85 || p == 99) return -3;  // d/d(own state) of rows F1-F3, F7, F8
+    if (p % 13 == 12) return -2;                                        // d/d(state s at node k+1)
+    if (p == 87 || p == 101) return -4;                                 // d/d(dphi), d/d(dCL) of rows F7, F8
+    return -1;
+}
+
 struct FgConst {
     int form, ts, wind, nb;
     int n, neF, neG;

@@ -73,7 +73,11 @@ constexpr int UNIT = TOLCUDA_UNIT;     // records per dense run = per bulk copy
 constexpr int PADW = TOLCUDA_PADW;     // doubles between runs (even: runs stay 16-byte aligned)
 constexpr int USTR = UNIT * REC + PADW;                     // run stride
 constexpr int BUF_LEN = (NPP / UNIT) * USTR;
-constexpr int TILE_LEN = NBUF * BUF_LEN;
+// + 16 doubles of slack: when the records of a trajectory start 8 mod 16 in global memory (odd ts, or an odd
+// leading dimension) the slots are used shifted by one double, so that all but the first and the last double of
+// a pass still form one 16-byte aligned bulk copy (see the drain in tile_eval); 16 keeps the tiles 128-byte aligned
+constexpr int TILE_SLACK = 16;
+constexpr int TILE_LEN = NBUF * BUF_LEN + TILE_SLACK;
 constexpr int SX_LEN = 368;            // a warp's x slice: slot for x[11*k0] + 33 nodes = 364 doubles (tile stays 128-byte aligned)
 static_assert(NPP % UNIT == 0 && 32 % NPP == 0 && PADW % 2 == 0 && NBUF * NPP <= 32, "record buffer layout");
 constexpr int WARP_SMEM = SX_LEN + TILE_LEN;        // kernel A
@@ -89,19 +93,44 @@ constexpr int MODE_PLAIN = 0, MODE_SUMMARY = 1, MODE_COMPACT = 2;
 constexpr int MODE_JVP = 3, MODE_VJP = 4;
 __host__ __device__ constexpr bool mode_is_op(int mode) { return mode == MODE_JVP || mode == MODE_VJP; }
 
-// What record position p (row s = p / 13, column j = p % 13: 0 = dt, 1..11 = component j-1 of node k, 12 =
-// component s of node k+1) holds: >= 0 index into the window's NVAR x-dependent values (the positions
-// record_store writes), -1: 0, -2: +1, -3: -1, -4: -dt (the positions tile_init / record_store write)
-__host__ __device__ constexpr int rec_kind(int p) {
-    constexpr int pos[TOLCUDA_NVAR] = {0,  4,  5,  6,  13, 17, 18, 19, 26, 30, 31, 39, 43, 44, 45, 47,
-                                       50, 52, 56, 57, 58, 59, 60, 65, 69, 70, 71, 72, 73, 78, 91};
+// Kernel experiment switches (bits 2.. of the kernels' needG argument: 4 = stage but do not store G, 8 = no
+// trigonometry, 16 = no Jacobian arithmetic) exist only in the experiments build (make exp -> libtolcuda_exp.so,
+// tools/kbench.py); in the release library they are compiled out and the public flags that would reach them are
+// rejected (tolcuda_api.cpp).
+#ifdef TOLCUDA_EXPERIMENTS
+#define EXP_SWITCH(needG, bit) ((needG) & (bit))
+#else
+#define EXP_SWITCH(needG, bit) 0
+#endif
+
+// Programmatic dependent launch (FgLaunch::pdl).  Every CTA releases the NEXT launch on the stream as soon as it
+// has started (griddepcontrol.launch_dependents), so the next grid's CTAs move into SMs the tail of this grid has
+// left instead of waiting for its last CTA.  A grid launched as a dependent reads only x before its first global
+// store; there it waits for the preceding grid to have completed (griddepcontrol.wait, FLOW_WAIT) -- unless the
+// caller has declared the outputs of the two launches disjoint, in which case the two grids simply overlap.
+// Both instructions are no-ops in a launch without the attribute.
+constexpr int FLOW_WAIT = 1;
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// record position -> content: tolcuda_rec_kind (fg_const.h), the table compact.cpp and expand_kernel.cu use too
+__host__ __device__ constexpr int rec_kind(int p) { return tolcuda_rec_kind(p); }
+// the positions record_store / tile_init write by hand, checked against that table
+constexpr bool record_slots_match_table() {
+    constexpr int var_pos[TOLCUDA_NVAR] = {0,  4,  5,  6,  13, 17, 18, 19, 26, 30, 31, 39, 43, 44, 45, 47,
+                                           50, 52, 56, 57, 58, 59, 60, 65, 69, 70, 71, 72, 73, 78, 91};
     for (int i = 0; i < TOLCUDA_NVAR; i++)
-        if (pos[i] == p) return i;
-    if (p == 1 || p == 15 || p == 29 || p == 85 || p == 99) return -3;
-    if (p % 13 == 12) return -2;
-    if (p == 87 || p == 101) return -4;
-    return -1;
+        if (rec_kind(var_pos[i]) != i) return false;
+    int nvar = 0;
+    for (int p = 0; p < TOLCUDA_REC; p++) {
+        const int kd = rec_kind(p);
+        nvar += kd >= 0;
+        const bool minus1 = p == 1 || p == 15 || p == 29 || p == 85 || p == 99, plus1 = p % 13 == 12;
+        if ((kd == -3) != minus1 || (kd == -2) != plus1 || (kd == -4) != (p == 87 || p == 101)) return false;
+    }
+    return nvar == TOLCUDA_NVAR;
 }
+static_assert(record_slots_match_table(), "record_store / tile_init disagree with tolcuda_rec_kind (fg_const.h)");
 template <int P>
 __device__ __forceinline__ double rec_value(const double *v, const double mdt) {
     constexpr int kd = rec_kind(P);
@@ -233,12 +262,20 @@ __device__ __forceinline__ void bulk_wait_read() {
 // 1182, 1204); everything x-dependent is zeroed here and written per window by record_store.
 // offset of record slot q (0 .. NPP-1) within a record buffer
 __device__ __forceinline__ int slot_offset(const int q) { return (q / UNIT) * USTR + (q % UNIT) * REC; }
-// lanes 0 .. NBUF*NPP-1 each prepare one record slot: zeros, then the 13 structural +-1 entries
-__device__ __forceinline__ void tile_init(double *tile, const int lane) {
+// lanes 0 .. NBUF*NPP-1 each prepare one record slot: zeros, then the 13 structural +-1 entries.
+// mis = 1: the slots sit one double further (records that start 8 mod 16 in global memory)
+__device__ __forceinline__ void tile_init(double *tile, const int lane, const int mis) {
     if (lane >= NBUF * NPP) return;
-    double *rec = tile + (lane / NPP) * BUF_LEN + slot_offset(lane % NPP);
+    double *rec = tile + (lane / NPP) * BUF_LEN + slot_offset(lane % NPP) + mis;
+    if (mis) {
+        rec[0] = 0.0;
 #pragma unroll
-    for (int j = 0; j < REC; j += 2) st2(rec + j, 0.0, 0.0);
+        for (int j = 1; j < REC - 1; j += 2) st2(rec + j, 0.0, 0.0);
+        rec[REC - 1] = 0.0;
+    } else {
+#pragma unroll
+        for (int j = 0; j < REC; j += 2) st2(rec + j, 0.0, 0.0);
+    }
     rec[1] = -1.0;   // F1 d/dx
     rec[15] = -1.0;  // F2 d/dy
     rec[29] = -1.0;  // F3 d/dz
@@ -275,6 +312,36 @@ __device__ __forceinline__ void record_store(double *rec, const double *v, const
     st2(rec + 86, 0.0, mdt);
     rec[91] = v[30];  // F8: dt, d/ddCL = -dt            :1183-1184
     st2(rec + 100, 0.0, mdt);
+}
+
+// the same entries into a slot that starts 8 mod 16: pairs are the (odd, even) neighbours
+__device__ __forceinline__ void record_store_shifted(double *rec, const double *v, const double mdt) {
+    rec[0] = v[0];
+    rec[4] = v[1];
+    st2(rec + 5, v[2], v[3]);
+    rec[13] = v[4];
+    st2(rec + 17, v[5], v[6]);
+    rec[19] = v[7];
+    rec[26] = v[8];
+    rec[30] = v[9];
+    rec[31] = v[10];
+    rec[39] = v[11];
+    st2(rec + 43, v[12], v[13]);
+    rec[45] = v[14];
+    rec[47] = v[15];
+    rec[50] = v[16];
+    rec[52] = v[17];
+    rec[56] = v[18];
+    st2(rec + 57, v[19], v[20]);
+    st2(rec + 59, v[21], v[22]);
+    rec[65] = v[23];
+    st2(rec + 69, v[24], v[25]);
+    st2(rec + 71, v[26], v[27]);
+    rec[73] = v[28];
+    rec[78] = v[29];
+    rec[87] = mdt;
+    rec[91] = v[30];
+    rec[101] = mdt;
 }
 
 // ---- wind model 3: trilinear interpolation of the cached wind cube, src/problem.cpp:544-695 -------------
@@ -353,14 +420,14 @@ __device__ __forceinline__ void wind_cube(const FgConst &c, const double xn, con
 // sx: the warp's staged x slice (slot 0 = x[11*k0], node j of the slice at sx[1+11j]).  Once every lane
 // has its window in registers the slice is dead and serves as staging area for F and the objective row.
 // tile: the warp's NBUF x NPP record slots, constants already in place (tile_init).
-// needG carries two experiment switches in bits 2 and 3 (tools/kbench.py): 4 = stage but do not store
-// G, 8 = no trigonometry.
+// dep_wait: this is the warp's first tile of a launch that may have started before the preceding launch on the
+// stream had finished (pdl_wait before the first global store).
 template <int FORM, int WIND, int MODE>
 __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *tile, const uint32_t tile_s, const double dt,
                                           const int k0, const int nk, const int lane,
                                           double *__restrict__ Fb, double *__restrict__ Gb,
                                           const int needF, const int needG, TileSums &ts_out,
-                                          const double *aux = nullptr) {
+                                          const bool dep_wait, int &tile_mis, const double *aux = nullptr) {
     double &sumT = ts_out.sumT, &sump = ts_out.sump;
     constexpr bool OP = mode_is_op(MODE);
     if (MODE == MODE_JVP) {  // the window's slice of d (the G pointer) into the unused record buffer
@@ -388,7 +455,7 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
 
     // ---- shared sub-expressions of the window ----
     double sc, cc, sg, cg, sp, cp;
-    if (needG & 8) {
+    if (EXP_SWITCH(needG, 8)) {
         sc = sg = sp = 0.6, cc = cg = cp = 0.8;
     } else {
         sincos(chi, &sc, &cc);
@@ -513,6 +580,7 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
         ts_out.dmax = m, ts_out.dssq = q;
     }
     __syncwarp();  // every lane has read its window: the slice is dead, sx becomes the staging area
+    if (dep_wait) pdl_wait();  // nothing has been stored so far
 
     if (needF && !OP) {
         double *fs = sx + F_LD * lane;
@@ -556,7 +624,7 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
 
     // ---- Jacobian rows, src/problem.cpp:1074-1192 ----
     double v[NVAR];
-    if (needG & 16) {  // experiment switch: no Jacobian arithmetic, the drain alone
+    if (EXP_SWITCH(needG, 16)) {  // experiment switch: no Jacobian arithmetic, the drain alone
 #pragma unroll
         for (int i = 0; i < NVAR; i++) v[i] = Va + (double)i;
     } else {
@@ -739,8 +807,20 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
     // ---- drain: passes of NPP windows through the record buffer(s), whole records to global ----
     // Pass g (windows k0+NPP*g ..) fills buffer g % NBUF once the TMA unit has read what the buffer held
     // before; lane 0 issues the pass's bulk copies (one per dense run of UNIT records) as one bulk group.
+    // Records that start 8 mod 16 in global memory (R0 is odd for odd ts; odd leading dimensions) are staged one
+    // double further into the slots: all but the first and the last double of a pass then form one 16-byte
+    // aligned bulk copy, and two lanes store those two doubles.
     double *Grec = Gb + c.R0 + (size_t)REC * k0;  // record of window k0
-    const bool bulk = (reinterpret_cast<uintptr_t>(Grec) & 15) == 0;
+    const int mis = (int)(reinterpret_cast<uintptr_t>(Grec) >> 3) & 1;
+    constexpr bool SHIFTABLE = (UNIT == NPP);  // one dense run per pass (the default layout)
+    const bool bulk = SHIFTABLE || !mis;
+    if (SHIFTABLE && mis != tile_mis) {  // the slots' constants are in place for the other alignment
+        __syncwarp();
+        tile_init(tile, lane, mis);
+        tile_mis = mis;
+        __syncwarp();
+    }
+    const int sh = SHIFTABLE ? mis : 0;
 #pragma unroll 1
     for (int g = 0; g < 32 / NPP; g++) {
         if (g * NPP >= nk) break;
@@ -750,17 +830,23 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
             __syncwarp();
         }
         if ((lane / NPP) == g) {
-            record_store(buf + slot_offset(lane & (NPP - 1)), v, mdt);
+            if (sh) record_store_shifted(buf + slot_offset(lane & (NPP - 1)) + 1, v, mdt);
+            else record_store(buf + slot_offset(lane & (NPP - 1)), v, mdt);
             // the writers make their generic-proxy stores visible to the async proxy (the TMA unit) ...
-            if (bulk && !(needG & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (bulk && !EXP_SWITCH(needG, 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
         const int nrec = min(NPP, nk - g * NPP);
         double *dst = Grec + (size_t)REC * NPP * g;
-        if (needG & 4) {
+        if (EXP_SWITCH(needG, 4)) {
             __syncwarp();
         } else if (bulk) {
             __syncwarp();  // ... and lane 0 issues the copies after all of them have done so
-            if (lane == 0) {
+            if (sh) {
+                // doubles [1, nrec*REC - 1) of the pass as one aligned copy; lanes 1 and 2 store the two ends
+                if (lane == 0) bulk_store(dst + 1, tile_s + 8 * ((g % NBUF) * BUF_LEN + 2), (nrec * REC - 2) * 8);
+                if (lane == 1) dst[0] = buf[1];
+                if (lane == 2) dst[nrec * REC - 1] = buf[nrec * REC];
+            } else if (lane == 0) {
 #pragma unroll
                 for (int u = 0; u < NPP / UNIT; u++)
                     if (u * UNIT < nrec)
@@ -973,9 +1059,10 @@ __device__ __forceinline__ void op_epilogue(const FgConst &c, const int lane, co
 constexpr int MAXPER = 4;
 template <int FORM, int WIND, int MAXT, int MINB, int MODE, bool LOOP>
 __global__ void __launch_bounds__(MAXT, MINB)
-fg_cta_kernel(const __grid_constant__ FgConst c, int B, int per_arg, const double *__restrict__ x, long ldx,
-               double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG,
+fg_cta_kernel(const __grid_constant__ FgConst c, int nrun, int per_arg, const double *__restrict__ x, long ldx,
+               double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG, int flow,
                double *__restrict__ S, long ldS) {
+    pdl_release();
     constexpr bool SUMM = (MODE == MODE_SUMMARY);
     extern __shared__ __align__(16) double smem[];
     constexpr bool OP = mode_is_op(MODE);
@@ -993,8 +1080,12 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int B, int per_arg, const doubl
     double *wsm = smem + (size_t)warp * (nslice * SX_LEN + TILE_LEN);
     double *tile = wsm + nslice * SX_LEN;
     const uint32_t wsm_s = smem_addr(wsm), tile_s = wsm_s + 8 * nslice * SX_LEN;
-    const size_t b0 = (size_t)per * blockIdx.x;
-    const int ntraj = LOOP ? (int)min((size_t)per, (size_t)B - b0) : 1;
+    // CTAs [0, nrun) own runs of `per` consecutive trajectories, the CTAs behind them one trajectory each: the grid
+    // ends on short CTAs, so its tail drains in half the time (launch_cta_as sizes the two parts)
+    const int bid = blockIdx.x;
+    const bool run = LOOP && bid < nrun;
+    const size_t b0 = LOOP ? (run ? (size_t)per * bid : (size_t)per * nrun + (size_t)(bid - nrun)) : (size_t)bid;
+    const int ntraj = run ? per : 1;
     const int k0 = 32 * warp;
     const int nk = min(32, ts - k0);
     const int cnt = 1 + PX * (nk + 1);           // doubles of a slice
@@ -1007,7 +1098,11 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int B, int per_arg, const doubl
         n0_nx = __ldg(xw - (size_t)PX * k0 + 1 + lane);
         ne_nx = __ldg(xw - (size_t)PX * k0 + (size_t)PX * ts + 1 + lane);
     }
-    if (needG && !OP) tile_init(tile, lane);
+    // alignment of this warp's records in the run's first trajectory (tile_eval re-initialises the slots if a
+    // later trajectory's differs: odd leading dimension)
+    int tile_mis = (int)(reinterpret_cast<uintptr_t>(G + b0 * ldG + c.R0 + (size_t)REC * k0) >> 3) & 1;
+    if (UNIT != NPP) tile_mis = 0;
+    if (needG && !OP) tile_init(tile, lane, tile_mis);
     if (tid < MAXPER) arrivals[tid] = 0;
     __syncthreads();
 #pragma unroll 1
@@ -1035,7 +1130,7 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int B, int per_arg, const doubl
             __syncwarp();
         }
         tile_eval<FORM, WIND, MODE>(c, wsm + slot * SX_LEN, tile, tile_s, dt, k0, nk, lane, Fb, Gb, needF, needG, tsum,
-                                    OP ? tile : nullptr);
+                                    t == 0 && (flow & FLOW_WAIT), tile_mis, OP ? tile : nullptr);
         __syncwarp();
         const double sumT = warp_sum(tsum.sumT);
         const double sump = FORM == TOLCUDA_FORM_S10 ? warp_sum(tsum.sump) : 0.0;
@@ -1086,8 +1181,9 @@ constexpr int LWARPS = 8;
 template <int FORM, int WIND, int MODE>
 __global__ void __launch_bounds__(LWARPS * 32, 2)
 fg_long_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, long ldx,
-               double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG,
+               double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG, int flow,
                double *__restrict__ S, long ldS) {
+    pdl_release();
     constexpr bool SUMM = (MODE == MODE_SUMMARY);
     extern __shared__ __align__(16) double smem[];
     constexpr bool OP = mode_is_op(MODE);
@@ -1111,7 +1207,8 @@ fg_long_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, 
         n0 = __ldg(xb + 1 + lane);
         ne = __ldg(xb + (size_t)PX * ts + 1 + lane);
     }
-    if (needG && !OP) tile_init(tile, lane);
+    int tile_mis = (UNIT == NPP) ? (int)(reinterpret_cast<uintptr_t>(Gb + c.R0) >> 3) & 1 : 0;  // REC*k0 is even
+    if (needG && !OP) tile_init(tile, lane, tile_mis);
     if (tid == 0) arrivals = 0;
     __syncthreads();
     double accT = 0.0, accp = 0.0, accm = 0.0, accq = 0.0;
@@ -1130,7 +1227,7 @@ fg_long_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, 
             __syncwarp();
         }
         tile_eval<FORM, WIND, MODE>(c, wsm + slot * SX_LEN, tile, tile_s, dt, 32 * j, min(32, ts - 32 * j), lane, Fb, Gb,
-                                    needF, needG, tsum, OP ? tile : nullptr);
+                                    needF, needG, tsum, j == warp && (flow & FLOW_WAIT), tile_mis, OP ? tile : nullptr);
         __syncwarp();
         accT += tsum.sumT;
         accp += tsum.sump;
@@ -1173,8 +1270,21 @@ fg_long_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, 
                             MODE == MODE_COMPACT ? NVAR : REC);
 }
 
+// one launch, optionally as a programmatic dependent of the launch before it on the stream (FgLaunch::pdl)
+template <class Kern, class... Args>
+cudaError_t launch_kernel(Kern kern, const int grid, const int nthr, const size_t smem, const FgLaunch &L, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3((unsigned)nthr);
+    cfg.dynamicSmemBytes = smem, cfg.stream = L.stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at, cfg.numAttrs = L.pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 template <int FORM, int WIND, int MAXT, int MINB, int MODE, bool LOOP>
-cudaError_t launch_cta_as(const FgLaunch &L, const int per) {
+cudaError_t launch_cta_as(const FgLaunch &L, const int per, const int nsingle) {
     auto kern = fg_cta_kernel<FORM, WIND, MAXT, MINB, MODE, LOOP>;
     const int nthr = 32 * ((L.c->ts + 31) / 32);
     const size_t smem = sizeof(double) * (size_t)(nthr / 32) * ((per > 1 ? 2 : 1) * SX_LEN + TILE_LEN);
@@ -1186,18 +1296,26 @@ cudaError_t launch_cta_as(const FgLaunch &L, const int per) {
         if (e != cudaSuccess) return e;
         done.store(smem, std::memory_order_release);
     }
-    kern<<<(L.B + per - 1) / per, nthr, smem, L.stream>>>(*L.c, L.B, per, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG, L.S, L.ldS);
-    return cudaGetLastError();
+    const int nrun = LOOP ? (L.B - nsingle) / per : 0;  // nsingle makes this exact (launch_cta)
+    const int grid = LOOP ? nrun + nsingle : L.B;
+    return launch_kernel(kern, grid, nthr, smem, L, *L.c, nrun, per, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG,
+                         L.pdl == 1 ? FLOW_WAIT : 0, L.S, L.ldS);
 }
 
-// runs of `per` trajectories per CTA pay off once the grid is many waves deep; small batches keep one
-// trajectory per CTA (more CTAs to spread over the SMs, and the cheaper straight-line instance)
+// Runs of `per` trajectories per CTA pay off once the grid is many waves deep (the x load and the CTA launch
+// leave the critical path, the slots' constants are written once per run); small batches keep one trajectory
+// per CTA (more CTAs to spread over the SMs, and the cheaper straight-line instance).  A grid of runs ends on
+// `tail` waves of single-trajectory CTAs: when the runs are exhausted the SMs' CTA slots free up over one run's
+// duration, and short CTAs fill them to a common end instead of leaving half of them idle for a whole run.
 template <int FORM, int WIND, int MAXT, int MINB, int MODE>
 cudaError_t launch_cta(const FgLaunch &L) {
     int per = L.per < 1 ? 1 : (L.per > MAXPER ? MAXPER : L.per);
-    if (L.per_auto && L.B < 48 * L.sm_count) per = 1;
-    return per == 1 ? launch_cta_as<FORM, WIND, MAXT, MINB, MODE, false>(L, 1)
-                    : launch_cta_as<FORM, WIND, MAXT, MINB, MODE, true>(L, per);
+    if (L.per_auto && L.B < L.per_min_waves * MINB * L.sm_count) per = 1;
+    if (per == 1) return launch_cta_as<FORM, WIND, MAXT, MINB, MODE, false>(L, 1, 0);
+    long nsingle = (long)(L.tail_waves_x4 * MINB * L.sm_count) / 4;
+    if (nsingle > L.B) nsingle = L.B;
+    nsingle += (L.B - nsingle) % per;
+    return launch_cta_as<FORM, WIND, MAXT, MINB, MODE, true>(L, per, (int)nsingle);
 }
 
 template <int FORM, int WIND, int MODE>
@@ -1216,8 +1334,8 @@ cudaError_t launch_long(const FgLaunch &L) {
         if (e != cudaSuccess) return e;
         done.store(smem, std::memory_order_release);
     }
-    kern<<<L.B, nthr, smem, L.stream>>>(*L.c, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG, L.S, L.ldS);
-    return cudaGetLastError();
+    return launch_kernel(kern, L.B, nthr, smem, L, *L.c, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG,
+                         L.pdl == 1 ? FLOW_WAIT : 0, L.S, L.ldS);
 }
 
 

@@ -26,7 +26,12 @@ struct FgLaunch {
     int kernel;    // 0/1 = kernel A (CTA per run of trajectories), 2 = kernel L (CTA per trajectory, tile loop; any ts)
     int lwarps;    // kernel L: warps per CTA (0: the count that balances the tiles)
     int per;       // kernel A: trajectories per CTA (1..4)
-    int per_auto;  // 1: small batches (B < 48 x SMs) use 1 regardless of `per`
+    int per_auto;  // 1: small batches (fewer than per_min_waves waves of CTAs) use 1 regardless of `per`
+    int per_min_waves;   // kernel A: batches below this many waves of single-trajectory CTAs run one trajectory per CTA
+    int tail_waves_x4;   // kernel A with runs: quarter-waves of single-trajectory CTAs the grid ends on
+    int pdl;       // 0: ordinary launch; 1: programmatic dependent launch, the kernel waits for the preceding launch on
+                   // the stream before its first store; 2: the same without the wait (outputs disjoint from the
+                   // preceding launch's reads and writes).  Never set for op != 0 (d / lambda are read early).
     int sm_count;  // SMs of the device
     int device;    // CUDA device ordinal the launch goes to (the current device)
     cudaStream_t stream;

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cctype>
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
@@ -55,10 +56,17 @@ struct tolcuda_ctx {
     tolcuda_config cfg;
     FgConst c;
     int kernel = 0;
-    int per = 2;  // kernel A: trajectories per CTA for large batches (TOLCUDA_PER fixes it for every batch size)
-    int per_auto = 1;
-    int lwarps = 0;  // kernel L: warps per CTA override (TOLCUDA_LWARPS; 0 = automatic)
-    int zero_copy = 1;  // single-trajectory path: kernel works on the mapped pinned block (TOLCUDA_ZEROCOPY=0: staged copies)
+    // launch shape (fg_kernels.cu launch_sel / launch_cta), see tolcuda_set_option.  The experiments build (make exp)
+    // also reads them from the environment: TOLCUDA_KERNEL, TOLCUDA_PER, TOLCUDA_PER_MIN_WAVES, TOLCUDA_TAIL_X4,
+    // TOLCUDA_LWARPS, TOLCUDA_ZEROCOPY, TOLCUDA_COMPACT, TOLCUDA_CHUNK_MB
+    int per = 2;             // trajectories per CTA for large batches
+    int per_auto = 1;        // ... and one per CTA below per_min_waves waves of CTAs
+    int per_min_waves = -1;  // -1: 24 (8 for launches that overlap their predecessor: tools/sweep.py, profiles/r2_sweep.txt)
+    int tail_waves_x4 = -1;  // quarter-waves of single-trajectory CTAs a grid of runs ends on; -1: 2, and 0 for
+                             // TOLCUDA_OVERLAP_DISJOINT launches (the next grid fills the tail anyway)
+    int lwarps = 0;  // kernel L: warps per CTA override (0 = automatic)
+    int zero_copy = 1;  // single-trajectory path: kernel works on the mapped pinned block (0: staged copies)
+    int chunk_mb = 32;  // host-pointer path: device bytes per lane (measured: 8..64 MB equally good, tools/expandbw.py)
     int sm_count = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::vector<int> iG, jG;
@@ -68,7 +76,7 @@ struct tolcuda_ctx {
     long ox = 0, oF = 0, oG = 0;
     // host-pointer batch path
     BatchLane lane[NLANES];
-    int compact_host = 1;  // host-pointer path: compact G across PCIe, expanded by host threads (TOLCUDA_COMPACT=0: full rows)
+    int compact_host = 1;  // host-pointer path: compact G across PCIe, expanded by host threads (0: full rows)
     int host_threads = 0;  // 0: HostPool::default_threads()
     std::unique_ptr<HostPool> pool;
     long launches = 0;
@@ -86,7 +94,8 @@ tolcuda_ctx *g_bound = nullptr;
 long round_up(long v, long m) { return (v + m - 1) / m * m; }
 
 int launch(tolcuda_ctx *h, cudaStream_t st, int B, const double *x, long ldx, double *F, long ldF,
-           double *G, long ldG, int needF, int needG, double *S = nullptr, long ldS = 0, int compact = 0, int op = 0) {
+           double *G, long ldG, int needF, int needG, double *S = nullptr, long ldS = 0, int compact = 0, int op = 0,
+           int pdl = 0) {
     FgLaunch L{};
     L.S = S, L.ldS = ldS;
     L.compact = compact;
@@ -99,6 +108,9 @@ int launch(tolcuda_ctx *h, cudaStream_t st, int B, const double *x, long ldx, do
     L.per = h->per;
     L.lwarps = h->lwarps;
     L.per_auto = h->per_auto;
+    L.pdl = op ? 0 : pdl;
+    L.per_min_waves = h->per_min_waves >= 0 ? h->per_min_waves : (L.pdl == 2 ? 8 : 24);
+    L.tail_waves_x4 = h->tail_waves_x4 >= 0 ? h->tail_waves_x4 : (L.pdl == 2 ? 0 : 2);
     L.sm_count = h->sm_count;
     L.device = h->cfg.device;
     L.stream = st;
@@ -343,11 +355,15 @@ int tolcuda_create(const tolcuda_config *cfg, tolcuda_handle *out) {
     }
     pattern_build(c.form, c.ts, h->iG, h->jG);
 
-    if (const char *env = std::getenv("TOLCUDA_KERNEL")) h->kernel = std::atoi(env);  // tests / tuning
-    if (const char *env = std::getenv("TOLCUDA_PER")) h->per = std::atoi(env), h->per_auto = 0;
-    if (const char *env = std::getenv("TOLCUDA_LWARPS")) h->lwarps = std::atoi(env);
-    if (const char *env = std::getenv("TOLCUDA_ZEROCOPY")) h->zero_copy = std::atoi(env);
-    if (const char *env = std::getenv("TOLCUDA_COMPACT")) h->compact_host = std::atoi(env);
+#ifdef TOLCUDA_EXPERIMENTS
+    for (const char *name : {"kernel", "per", "per_min_waves", "tail_x4", "lwarps", "zero_copy", "compact_host", "chunk_mb"}) {
+        std::string env = std::string("TOLCUDA_") + name;
+        for (char &ch : env) ch = (char)std::toupper((unsigned char)ch);
+        if (env == "TOLCUDA_ZERO_COPY") env = "TOLCUDA_ZEROCOPY";
+        if (env == "TOLCUDA_COMPACT_HOST") env = "TOLCUDA_COMPACT";
+        if (const char *v = std::getenv(env.c_str())) tolcuda_set_option(h, name, std::atol(v));
+    }
+#endif
     if (const char *env = std::getenv("TOLCUDA_DUMP_DIR")) h->dump_dir = env;
 
     int rc = 0;
@@ -610,8 +626,16 @@ int tolcuda_eval_batch_summary(tolcuda_handle h, int B, const double *x, long ld
                                double *G, long ldG, double *summary, long lds, int flags) {
     if (!h || B < 0 || (summary && lds < 4)) return TOLCUDA_EINVAL;
     const int needF = (flags & TOLCUDA_NEED_F) != 0;
-    // bits 16.. of flags: kernel experiment switches (undocumented, tools/kbench.py only)
+#ifdef TOLCUDA_EXPERIMENTS
+    // experiments build only: bits 16.. of flags are kernel experiment switches (tools/kbench.py)
     const int needG = (flags & TOLCUDA_NEED_G) ? (1 | (((flags >> 16) & 0xff) << 1)) : 0;
+#else
+    if (flags & ~TOLCUDA_FLAGS_ALL) {
+        set_error("tolcuda_eval_batch: unknown flag bits");
+        return TOLCUDA_EINVAL;
+    }
+    const int needG = (flags & TOLCUDA_NEED_G) != 0;
+#endif
     if (B == 0 || (!needF && !needG && !summary)) return 0;
     const FgConst &c = h->c;
     const long lenGc = compact_len(c.form, c.ts);
@@ -637,8 +661,13 @@ int tolcuda_eval_batch_summary(tolcuda_handle h, int B, const double *x, long ld
             host = !(at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged);
         }
     }
+    const int pdl = (flags & TOLCUDA_OVERLAP_DISJOINT) ? 2 : ((flags & TOLCUDA_OVERLAP) ? 1 : 0);
+    if (pdl && (host || !(flags & TOLCUDA_NO_SYNC))) {
+        set_error("tolcuda_eval_batch: TOLCUDA_OVERLAP needs device pointers and TOLCUDA_NO_SYNC");
+        return TOLCUDA_EINVAL;
+    }
     if (!host) {
-        int rc = launch(h, h->stream, B, x, ldx, F, ldF, G, ldG, needF, needG, summary, lds, compact_rows);
+        int rc = launch(h, h->stream, B, x, ldx, F, ldF, G, ldG, needF, needG, summary, lds, compact_rows, 0, pdl);
         if (rc) return rc;
         if (!(flags & TOLCUDA_NO_SYNC)) CU(cudaStreamSynchronize(h->stream));
         return 0;
@@ -656,11 +685,7 @@ int tolcuda_eval_batch_summary(tolcuda_handle h, int B, const double *x, long ld
     const long dldG = tolcuda_padded_ld(dev_compact ? lenGc : (long)c.neG);
     const long rowG = dev_compact ? lenGc : (long)c.neG;  // doubles of a G row that cross PCIe
     const size_t per_traj = sizeof(double) * (size_t)(dldx + dldF + dldG);
-    size_t budget = (size_t)32 << 20;  // device bytes per lane (measured: 8..64 MB equally good, tools/expandbw.py)
-    if (const char *env = std::getenv("TOLCUDA_CHUNK_MB")) {
-        long mb = std::atol(env);
-        if (mb > 0) budget = (size_t)mb << 20;
-    }
+    const size_t budget = (size_t)h->chunk_mb << 20;  // device bytes per lane
     int chunk = (int)std::max<size_t>(1, budget / per_traj);
     chunk = std::min(chunk, B);
     if (B > chunk && B < NLANES * chunk) chunk = (B + NLANES - 1) / NLANES;
@@ -821,6 +846,34 @@ int tolcuda_set_host_threads(tolcuda_handle h, int threads) {
     if (!h || threads < 0) return TOLCUDA_EINVAL;
     h->host_threads = threads;
     h->pool.reset();  // rebuilt with the new size by the next host-pointer batch call
+    return 0;
+}
+
+// Execution-strategy options: every value of every option produces the same bits in F and G.
+int tolcuda_set_option(tolcuda_handle h, const char *name, long value) {
+    if (!h || !name) return TOLCUDA_EINVAL;
+    const std::string k(name);
+    auto in = [&](long lo, long hi) { return value >= lo && value <= hi; };
+    bool ok = true;
+    if (k == "kernel") ok = in(0, 2), h->kernel = ok ? (int)value : h->kernel;
+    else if (k == "per") {
+        ok = in(0, 4);
+        if (ok && value == 0) h->per = 2, h->per_auto = 1;
+        else if (ok) h->per = (int)value, h->per_auto = 0;
+    } else if (k == "per_min_waves") ok = in(-1, 1 << 20), h->per_min_waves = ok ? (int)value : h->per_min_waves;
+    else if (k == "tail_x4") ok = in(-1, 64), h->tail_waves_x4 = ok ? (int)value : h->tail_waves_x4;
+    else if (k == "lwarps") ok = in(0, 8), h->lwarps = ok ? (int)value : h->lwarps;
+    else if (k == "zero_copy") ok = in(0, 1), h->zero_copy = ok ? (int)value : h->zero_copy;
+    else if (k == "compact_host") ok = in(0, 1), h->compact_host = ok ? (int)value : h->compact_host;
+    else if (k == "chunk_mb") ok = in(1, 4096), h->chunk_mb = ok ? (int)value : h->chunk_mb;
+    else {
+        set_error("tolcuda_set_option: unknown option " + k);
+        return TOLCUDA_EINVAL;
+    }
+    if (!ok) {
+        set_error("tolcuda_set_option: value out of range for " + k);
+        return TOLCUDA_EINVAL;
+    }
     return 0;
 }
 

@@ -10,6 +10,7 @@ from . import lib as _l
 G7, S10 = 7, 10
 NEED_F, NEED_G = 0x1, 0x2
 HOST_PTRS, DEVICE_PTRS, NO_SYNC, COMPACT_G, FULL_G_COPY = 0x10, 0x20, 0x40, 0x80, 0x100
+OVERLAP, OVERLAP_DISJOINT = 0x200, 0x400
 _FORM = {"G7": G7, "S10": S10, G7: G7, S10: S10}
 
 
@@ -196,16 +197,19 @@ class Evaluator:
         return self
 
     @classmethod
-    def from_golden(cls, g, device=0, wind_model=None):
-        """g: an opened tests/golden/*.npz fixture"""
+    def from_golden(cls, g, device=0, wind_model=None, options=None):
+        """g: an opened tests/golden/*.npz fixture; options: {name: value} for tolcuda_set_option"""
         wm = int(g["wind_model"]) if wind_model is None else wind_model
         ev = cls(str(g["mission"]), int(g["ts"]), g["ac"], g["gn"], g["goal_ned"], 1 if wm == 3 else wm, device)
+        for k, v in (options or {}).items():
+            ev.set_option(k, v)
         if wm == 3:
             ev.set_wind_grid(g["grid_x"], g["grid_y"], g["grid_z"], g["grid_v"], g["grid_datum"], g["grid_spacing"])
         return ev
 
     def _finish(self, L, device):
         self.L, self.device = L, device
+        self._stream_pinned = False  # True once the caller has chosen a stream (set_stream / use_own_stream)
         n, neF, neG = C.c_int(), C.c_int(), C.c_int()
         _l.check(L.tolcuda_dims(self.h, C.byref(n), C.byref(neF), C.byref(neG)))
         self.n, self.neF, self.neG = n.value, neF.value, neG.value
@@ -224,6 +228,19 @@ class Evaluator:
 
     def set_host_threads(self, threads):
         _l.check(self.L.tolcuda_set_host_threads(self.h, int(threads)))
+
+    def _follow_torch(self, t):
+        """Calls that take torch tensors run on torch's CURRENT stream of the tensors' device unless the caller has
+        chosen a stream: the context's own stream is non-blocking, so work torch has queued on the tensors (fills,
+        copies, slice assignments) would otherwise not be ordered against the kernels (include/tolcuda.h,
+        tolcuda_set_stream)."""
+        if not self._stream_pinned:
+            import torch
+            _l.check(self.L.tolcuda_set_stream(self.h, C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)))
+
+    def set_option(self, name, value):
+        """tolcuda_set_option: execution-strategy options (kernel, per, tail_x4, chunk_mb, ...); results never change"""
+        _l.check(self.L.tolcuda_set_option(self.h, name.encode(), int(value)))
 
     def close(self):
         if getattr(self, "h", None):
@@ -287,12 +304,15 @@ class Evaluator:
                                            F.strides[0] // 8, G.ctypes.data, G.strides[0] // 8, flags))
         return F, G
 
-    def eval_batch_device(self, X, F, G, needF=True, needG=True, sync=True, compact_rows=False):
-        """tolcuda_eval_batch with torch CUDA tensors [B, ld] (float64, row-contiguous)"""
+    def eval_batch_device(self, X, F, G, needF=True, needG=True, sync=True, compact_rows=False, overlap=0, extra_flags=0):
+        """tolcuda_eval_batch with torch CUDA tensors [B, ld] (float64, row-contiguous).  overlap (sync=False only):
+        1 = TOLCUDA_OVERLAP, 2 = TOLCUDA_OVERLAP_DISJOINT.  extra_flags: ORed in as is (tools/kbench.py with the
+        experiments build; the release library rejects unknown bits)"""
+        self._follow_torch(X)
         B = X.shape[0]
         flags = (NEED_F if needF else 0) | (NEED_G if needG else 0) | DEVICE_PTRS | (0 if sync else NO_SYNC)
         flags |= COMPACT_G if compact_rows else 0
-        flags |= (int(needG) >> 1) << 16  # experiment switches (tools/kbench.py)
+        flags |= (OVERLAP if overlap == 1 else 0) | (OVERLAP_DISJOINT if overlap == 2 else 0) | int(extra_flags)
         _l.check(self.L.tolcuda_eval_batch(self.h, B, X.data_ptr(), X.stride(0), F.data_ptr(), F.stride(0),
                                            G.data_ptr(), G.stride(0), flags))
 
@@ -307,22 +327,26 @@ class Evaluator:
     def expand_compact_device(self, Gc, G, sync=True):
         """tolcuda_expand_compact_g_device: compact rows (torch CUDA tensor [B, >= compact_len]) -> rows in
         coordinate order (torch CUDA tensor [B, >= neG]) on the context's stream"""
+        self._follow_torch(Gc)
         _l.check(self.L.tolcuda_expand_compact_g_device(self.h, Gc.shape[0], Gc.data_ptr(), Gc.stride(0), G.data_ptr(),
                                                         G.stride(0), 0 if sync else NO_SYNC))
 
     def repack_csc_device(self, G, Gcsc, sync=True):
         """tolcuda_repack_csc_device: rows in coordinate order -> rows in CSC order (torch CUDA tensors)"""
+        self._follow_torch(G)
         _l.check(self.L.tolcuda_repack_csc_device(self.h, G.shape[0], G.data_ptr(), G.stride(0), Gcsc.data_ptr(),
                                                   Gcsc.stride(0), 0 if sync else NO_SYNC))
 
     def jac_vec(self, X, D, Y, sync=True):
         """tolcuda_jac_vec: Y[b] = J(X[b]) D[b] without materialising G (torch CUDA tensors [B, >= n], [B, >= n],
         [B, >= neF])"""
+        self._follow_torch(X)
         _l.check(self.L.tolcuda_jac_vec(self.h, X.shape[0], X.data_ptr(), X.stride(0), D.data_ptr(), D.stride(0),
                                         Y.data_ptr(), Y.stride(0), 0 if sync else NO_SYNC))
 
     def jac_tvec(self, X, Lam, Z, sync=True):
         """tolcuda_jac_tvec: Z[b] = J(X[b])^T Lam[b] (torch CUDA tensors [B, >= n], [B, >= neF], [B, >= n])"""
+        self._follow_torch(X)
         _l.check(self.L.tolcuda_jac_tvec(self.h, X.shape[0], X.data_ptr(), X.stride(0), Lam.data_ptr(), Lam.stride(0),
                                          Z.data_ptr(), Z.stride(0), 0 if sync else NO_SYNC))
 
@@ -349,9 +373,11 @@ class Evaluator:
 
     def set_stream(self, cuda_stream_ptr):
         """cudaStream_t as an integer (torch: stream.cuda_stream; 0 = legacy default stream)"""
+        self._stream_pinned = True
         _l.check(self.L.tolcuda_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
     def use_own_stream(self):
+        self._stream_pinned = True
         _l.check(self.L.tolcuda_use_own_stream(self.h))
 
     def synchronize(self):

@@ -56,6 +56,7 @@ def load():
     L.tolcuda_compact_len.restype = C.c_long
     L.tolcuda_expand_compact_g.argtypes = [C.c_int, C.c_int, C.c_long, vp, C.c_long, vp, C.c_long, C.c_int]
     L.tolcuda_set_host_threads.argtypes = [vp, C.c_int]
+    L.tolcuda_set_option.argtypes = [vp, C.c_char_p, C.c_long]
     L.tolcuda_problem_pattern_csc.argtypes = [C.c_int, C.c_int, ip, ip, ip]
     L.tolcuda_repack_csc_device.argtypes = [vp, C.c_long, vp, C.c_long, vp, C.c_long, C.c_int]
     L.tolcuda_expand_compact_g_device.argtypes = [vp, C.c_long, vp, C.c_long, vp, C.c_long, C.c_int]

@@ -14,12 +14,7 @@ import tol_b200 as T  # noqa: E402
 for name in ("S10_tempest_ts200", "G7_skywalker_ts100", "S10_tempest_ts100_wind3", "S10_tempest_ts1"):
     g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
     for kernel, per in ((0, None), (0, 1), (0, 3), (2, None)):
-        os.environ["TOLCUDA_KERNEL"] = str(kernel)
-        if per is None:
-            os.environ.pop("TOLCUDA_PER", None)
-        else:
-            os.environ["TOLCUDA_PER"] = str(per)
-        ev = T.Evaluator.from_golden(g)
+        ev = T.Evaluator.from_golden(g, options={"kernel": kernel, "per": per or 0})
         B = 19
         X = T.synth.batch(g["x"][0], 5, 0, B)
         F, G = ev.eval_batch_host(X, full_copy=True)

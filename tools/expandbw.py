@@ -34,7 +34,7 @@ X = torch.zeros(B, padded_ld(n), dtype=torch.float64).pin_memory()
 T.synth.batch(g["x"][0], T.synth.SEED_S10, 0, B, out=X.numpy())
 F = torch.empty(B, padded_ld(neF), dtype=torch.float64).pin_memory()
 for mb in (1, 2, 4, 8, 16, 32, 64):
-    os.environ["TOLCUDA_CHUNK_MB"] = str(mb)
+    ev.set_option("chunk_mb", mb)
     for th in (4, 8, 16):
         ev.set_host_threads(th)
         for full in (False,):
