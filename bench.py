@@ -293,22 +293,10 @@ def measured_peak():
 
 
 def kernel_sass_hash(mission, wind, ts):
-    """sha256 of the bench kernel's SASS text (addresses stripped) in the library this run loaded: ties the stored
-    ncu traffic ratio to a kernel binary.  None when cuobjdump is not at hand."""
-    import hashlib
-    import re
-    import tol_b200 as T
-    form = 10 if mission == "S10" else 7
-    maxt, minb = (128, 4) if ts <= 128 else (256, 2)
-    sym = "fg_cta_kernelILi%dELi%dELi%dELi%dELi0ELb1EE" % (form, wind, maxt, minb)
-    try:
-        out = subprocess.run(["cuobjdump", "-sass", "-fun", sym, T.LIB_PATH], capture_output=True, text=True, timeout=120).stdout
-    except (OSError, subprocess.TimeoutExpired):
-        return None
-    body = [re.sub(r"/\*[0-9a-f]{4,}\*/", "", ln).strip() for ln in out.splitlines() if "/*" in ln and ";" in ln]
-    if len(body) < 100:
-        return None
-    return hashlib.sha256("\n".join(body).encode()).hexdigest()[:16]
+    """sha256 (16 hex digits) of the bench kernel's SASS in the library this run loaded: ties the stored ncu traffic
+    ratio to a kernel binary.  None when cuobjdump is not at hand."""
+    from tol_b200.sass import bench_kernel_pattern, kernel_sass_hash as h
+    return h(bench_kernel_pattern(mission, wind, ts))
 
 
 def ncu_traffic(wl_name, alg_bytes, sass_hash):

@@ -304,12 +304,50 @@ int tolcuda_enable_peer(int device, int peer);
 int tolcuda_stream_signal(tolcuda_handle h, void *flag, unsigned int value);
 int tolcuda_stream_wait(tolcuda_handle h, const void *flag, unsigned int value);
 
+/* Fused evaluate + gather: all B rows of F and G of a batch whose shards are evaluated on `world` GPUs, in the memory
+ * of ONE of them (rank `dst`), written there by the shards' own kernels over NVLink while they compute -- no send
+ * buffer, no collective.  The protocol of the primitives above in one place (gather.cpp), for a C/C++ driver with
+ * several devices (tolbatch --gather-gpu) and for one process per GPU alike.  Rank q owns the contiguous block of
+ * trajectory indices [q*ceil(B/world), ...).
+ *   tolcuda_gather_create   the gathering rank: allocates the buffer on its context's device (F rows | G rows |
+ *                           staging for the peers' compact rows | chunk flags); ipc_handle (may be NULL) receives the
+ *                           TOLCUDA_IPC_HANDLE_BYTES bytes other PROCESSES need
+ *   tolcuda_gather_attach   every other rank, on its own context: `owner` = the creating rank's gather handle when it
+ *                           lives in the same process (peer access is enabled), else NULL and `ipc_handle` = the bytes
+ *                           the owner exported
+ *   tolcuda_gather_send     a peer evaluates its shard (x: its rows on its device) in `chunks` launches; F goes to its
+ *                           final place, G as compact rows into the staging region, each chunk followed by a
+ *                           stream-ordered flag in the owner's memory.  Asynchronous (tolcuda_synchronize to wait).
+ *   tolcuda_gather_collect  the owner evaluates its own shard in place and expands every peer chunk into rows in
+ *                           coordinate order as soon as its flag arrives (no host in between); returns, after
+ *                           synchronising, the device pointers and leading dimensions of the B rows.
+ * All ranks call send / collect once per evaluation, with the same `chunks` (1..16).  A peer must not start the NEXT
+ * send before the owner's collect of this one has returned (in one process: program order; across processes: a
+ * barrier).  The rows are bit for bit those of a single GPU evaluating the whole batch. */
+typedef struct tolcuda_gather *tolcuda_gather_handle;
+int tolcuda_gather_create(tolcuda_handle h, long B, int world, int dst, tolcuda_gather_handle *out,
+                          unsigned char *ipc_handle);
+int tolcuda_gather_attach(tolcuda_handle h, long B, int world, int rank, int dst, tolcuda_gather_handle owner,
+                          const unsigned char *ipc_handle, tolcuda_gather_handle *out);
+int tolcuda_gather_send(tolcuda_gather_handle g, const double *x, long ldx, int chunks);
+int tolcuda_gather_collect(tolcuda_gather_handle g, const double *x, long ldx, int chunks, double **F, long *ldF,
+                           double **G, long *ldG);
+int tolcuda_gather_buffer(tolcuda_gather_handle g, void **base, size_t *bytes); /* the owner's buffer as mapped here */
+int tolcuda_gather_close(tolcuda_gather_handle g);
+/* synchronous copies between host memory and memory of `device` (plain wrappers, like tolcuda_host_alloc) */
+int tolcuda_copy_to_device(int device, void *dst, const void *src, size_t bytes);
+int tolcuda_copy_to_host(int device, void *dst, const void *src, size_t bytes);
+
 /* smallest multiple of 16 doubles (128 bytes) that holds `len` doubles */
 long tolcuda_padded_ld(long len);
 
 /* run the context's single-trajectory and device-pointer work on a caller-owned cudaStream_t (e.g.
  * torch's current stream) so that the caller's CUDA events bracket the kernels.  NULL is the legacy
- * default stream, as everywhere in CUDA; tolcuda_use_own_stream goes back to the context's own. */
+ * default stream, as everywhere in CUDA; tolcuda_use_own_stream goes back to the context's own.
+ * The context's own stream is created cudaStreamNonBlocking: it is NOT ordered against the legacy default stream or
+ * any other stream.  With device pointers the caller orders its producers of x and its consumers (or earlier
+ * writers, e.g. a memset) of F/G against the stream in use -- by handing over its own stream here, by
+ * tolcuda_synchronize, or by events. */
 int tolcuda_set_stream(tolcuda_handle h, void *cuda_stream);
 int tolcuda_use_own_stream(tolcuda_handle h);
 int tolcuda_synchronize(tolcuda_handle h);

@@ -33,7 +33,8 @@ def perturb(x0, seed):
 # name, mission, aircraft, enu, goal(E,N,U,R), ts(None = shipped 100), gains override, seed0, samples
 CASES = [
     ("G7_skywalker_ts100", "G7", "skywalker", (0, 0, 70), (400, 0, 0, 0), None, None, 20260000, 4),
-    ("S10_tempest_ts100", "S10", "tempest", (0, 0, 70), (0, -100, 0, 100), None, None, 20270000, 4),
+    # BASELINE.json configs[1] / SURVEY.md 8d config 2: the reference x0 and 16 seeded perturbations
+    ("S10_tempest_ts100", "S10", "tempest", (0, 0, 70), (0, -100, 0, 100), None, None, 20270000, 17),
     ("S10_tempest_ts200", "S10", "tempest", (0, 0, 70), (0, -100, 0, 100), 200, None, 20270000, 2),
     ("G7_skywalker_ts200", "G7", "skywalker", (0, 0, 70), (400, 0, 0, 0), 200, None, 20260000, 2),
     ("G7_tempestwill_ts7_gains", "G7", "tempest_will", (5, -3, 40), (250, -300, 20, 0), 7,

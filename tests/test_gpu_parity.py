@@ -35,6 +35,33 @@ def test_single_trajectory_matches_reference(name):
     ev.close()
 
 
+def test_config2_reference_x0_and_16_perturbations_through_the_callback():
+    """BASELINE.json configs[1] / SURVEY.md 8d config 2: S10, tempest, ts = 100 -- the reference's own initial guess and
+    16 seeded perturbations, every one through the exported snOptA callback DEFINEGusrfg_ (reference
+    src/DefineFG.cpp:9-48) against the rows the unmodified reference wrote for the same states: pattern as integer
+    arrays, values within 1e-14 + 1e-12*|ref|, the 11 entries the reference leaves uninitialised masked (0.0 here)"""
+    g = load_golden("S10_tempest_ts100")
+    assert g["x"].shape[0] == 17 and int(g["ts"]) == 100 and str(g["aircraft"]) == "tempest"
+    for s in range(1, 17):  # the fixture's states ARE the section-8d perturbations of x0
+        assert np.array_equal(g["x"][s], T.synth.perturb(g["x"][0], int(g["seed0"]) + s - 1))
+    ev = T.Evaluator.from_golden(g)
+    i, j = ev.pattern()
+    assert i.dtype == np.int32 and np.array_equal(i, g["iGfun"]) and np.array_equal(j, g["jGvar"])
+    mask = g["ub_mask"]
+    for s in range(17):
+        st, F, G = ev.usrfun(g["x"][s], 1, 1)
+        assert st == 0
+        assert_parity(F, g["F"][s], "config 2 state %d F" % s)
+        assert_parity(G, g["G"][s], "config 2 state %d G" % s)
+        assert (G[mask] == 0.0).all()
+        if s % 4 == 0:  # F alone and G alone, as SNOPT asks for them during a line search
+            st, F1, G1 = ev.usrfun(g["x"][s], 1, 0)
+            assert st == 0 and np.array_equal(F1, F) and np.isnan(G1).all()
+            st, F1, G1 = ev.usrfun(g["x"][s], 0, 1)
+            assert st == 0 and np.array_equal(G1, G) and np.isnan(F1).all()
+    ev.close()
+
+
 @pytest.mark.parametrize("name", ["S10_tempest_ts100", "G7_skywalker_ts100", "S10_tempesteric_ts33"])
 def test_snopta_callback_drop_in(name):
     """DEFINEGusrfg_ with SNOPT's argument list; needF/needG honoured; Status untouched on success"""
@@ -334,6 +361,16 @@ def test_tolbatch_driver_end_to_end(tmp_path):
         assert sm["summary_only"] is True and sm["nonfinite"] == 0
         for a, b in zip(sm["trajectories"], d["trajectories"]):
             assert a["objective"] == b["objective"] and a["max_abs_defect"] == b["max_abs_defect"]
+        # the same batch gathered on ONE GPU by the shards' own kernels (tolcuda_gather_*, the C form of
+        # tol_b200.dist.eval_and_gather_peer): on every GPU count present, every choice of the gathering GPU, the
+        # rows in its memory are bit for bit the rows of the host gather (tolbatch compares them and says so)
+        ngpu = torch.cuda.device_count()
+        for G_ in sorted({1, min(2, ngpu), ngpu}):
+            for D_ in sorted({0, G_ - 1}):
+                r = subprocess.run([exe] + args + ["--root", root, "--batch", "301", "--steps", "2", "--gpus", str(G_),
+                                                   "--gather-gpu", str(D_)], capture_output=True, text=True, timeout=180)
+                assert r.returncode == 0, r.stdout + r.stderr
+                assert "gather on GPU %d" % D_ in r.stdout and "rows bit-identical to the host gather: yes" in r.stdout
             assert a["max_abs_boundary"] <= b["max_abs_boundary"]
 
 
@@ -767,7 +804,6 @@ def test_peer_buffer_rows_on_one_gpu():
     buf = D.open_peer_buffer(ev, B, 0, staged=False)
     assert len(buf.handle) == T.evaluator.IPC_HANDLE_BYTES and any(buf.handle)
     buf.tensor(0, 1, B * (ldF + ldG)).fill_(float("nan"))
-    assert not buf.tensor(B * (ldF + ldG), 1, D.FLAG_BYTES // 8).any()  # the chunk flags start at zero
     F, G, kept = D.eval_and_gather_peer(ev, X, B, out=buf)
     assert kept is buf and F.shape == (B, ldF) and G.shape == (B, ldG)
     Fd = torch.empty(B, ev.neF, dtype=torch.float64, device="cuda")

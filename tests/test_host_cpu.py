@@ -326,6 +326,14 @@ def test_tolbatch_fails_loudly_on_bad_arguments_and_without_a_device():
     assert r.returncode == 2 and "unknown option --bogus" in r.stderr
     r = subprocess.run([exe] + pos + ["--perturb", "abc"], capture_output=True, text=True)
     assert r.returncode == 2 and "--perturb wants REL,ABS" in r.stderr
+    # sizes that would index an empty batch, allocate a negative size or report a timing of no step
+    for opt, val, msg in (("--batch", "0", "--batch must be at least 1"), ("--batch", "-5", "--batch must be at least 1"),
+                          ("--steps", "0", "--steps must be at least 1"), ("--nresults", "-1", "--nresults must not be negative"),
+                          ("--gpus", "-2", "--gpus must not be negative")):
+        r = subprocess.run([exe] + pos + [opt, val], capture_output=True, text=True)
+        assert r.returncode == 2 and msg in r.stderr and r.stdout == "", (opt, val, r.stderr)
+    r = subprocess.run([exe] + pos + ["--gather-gpu", "0", "--summary-only"], capture_output=True, text=True)
+    assert r.returncode == 2 and "--gather-gpu" in r.stderr
     if not torch.cuda.is_available():
         r = subprocess.run([exe] + pos + ["--batch", "4"], capture_output=True, text=True)
         assert r.returncode == 2 and "failed" in r.stderr and r.stdout == ""

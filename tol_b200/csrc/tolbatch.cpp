@@ -14,6 +14,10 @@
 //                                             summary the kernels compute on the fly comes back
 //                                             (tolcuda_eval_batch_summary without F or G: objective, worst defect,
 //                                             worst boundary violation), no F/G rows on the host
+//            [--gather-gpu D]                 after the host gather: the same batch once more with every GPU's shard
+//                                             written straight into GPU D's memory by the shards' own kernels
+//                                             (tolcuda_gather_*: NVLink peer stores, no host in between), timed, and
+//                                             compared bit for bit with the rows of the host gather
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -31,7 +35,7 @@ namespace {
 struct Args {
     double enu[3] = {0, 0, 0}, goal[4] = {0, 0, 0, 0};
     std::string aircraft, mission, root = "./", xfile, json, results;
-    int ts = 0, batch = 4096, gpus = 0, steps = 3, nresults = 4;
+    int ts = 0, batch = 4096, gpus = 0, steps = 3, nresults = 4, gather_gpu = -1;
     bool summary_only = false;
     uint64_t seed = 1;
     double rel = 0.05, abs_ = 0.01;
@@ -62,7 +66,8 @@ void check(int rc, const char *what) {
 Args parse(int argc, char **argv) {
     if (argc < 10)
         die("usage: tolbatch E N U Eg Ng Ug Rg aircraft mission [--root DIR/] [--ts N] [--batch B] [--gpus G] "
-            "[--seed S] [--perturb REL,ABS] [--x-file F] [--steps K] [--json OUT] [--results DIR [--nresults K]] [--summary-only]");
+            "[--seed S] [--perturb REL,ABS] [--x-file F] [--steps K] [--json OUT] [--results DIR [--nresults K]] [--summary-only] "
+            "[--gather-gpu D]");
     Args a;
     for (int i = 0; i < 3; i++) a.enu[i] = std::atof(argv[1 + i]);  // as src/arguments.cpp:35-41 (atof)
     for (int i = 0; i < 4; i++) a.goal[i] = std::atof(argv[4 + i]);
@@ -85,11 +90,18 @@ Args parse(int argc, char **argv) {
         else if (k == "--results") a.results = val();
         else if (k == "--nresults") a.nresults = std::atoi(val());
         else if (k == "--summary-only") a.summary_only = true;
+        else if (k == "--gather-gpu") a.gather_gpu = std::atoi(val());
         else if (k == "--perturb") {
             if (std::sscanf(val(), "%lf,%lf", &a.rel, &a.abs_) != 2) die("--perturb wants REL,ABS");
         } else die("unknown option " + k);
     }
     if (!a.root.empty() && a.root.back() != '/') a.root += '/';  // the reference concatenates paths
+    if (a.batch < 1) die("--batch must be at least 1");
+    if (a.steps < 1) die("--steps must be at least 1");
+    if (a.nresults < 0) die("--nresults must not be negative");
+    if (a.gpus < 0) die("--gpus must not be negative");
+    if (a.ts < 0) die("--ts must not be negative");
+    if (a.gather_gpu >= 0 && a.summary_only) die("--gather-gpu gathers F and G rows: not available with --summary-only");
     return a;
 }
 
@@ -198,6 +210,57 @@ int main(int argc, char **argv) {
                 "non-finite values %ld\n",
                 1e3 * best, (double)B * ts / best, obj[0], worst_defect, nonfinite);
 
+    // ---- the same batch gathered on ONE GPU by the shards' own kernels (tolcuda_gather_*), against the host gather
+    bool gather_same = true;
+    if (a.gather_gpu >= 0) {
+        const int D = a.gather_gpu;
+        if (D >= G) die("--gather-gpu " + std::to_string(D) + ": only " + std::to_string(G) + " GPU(s) in use");
+        const int per = (B + G - 1) / G;
+        std::vector<double *> dx(G, nullptr);
+        for (int g = 0; g < G; g++) {
+            const int b0 = std::min(B, g * per), b1 = std::min(B, b0 + per);
+            if (b1 <= b0) continue;
+            check(tolcuda_device_alloc(g, sizeof(double) * ldx * (b1 - b0), (void **)&dx[g]), "device x");
+            check(tolcuda_copy_to_device(g, dx[g], X + (size_t)b0 * ldx, sizeof(double) * ldx * (b1 - b0)), "x to device");
+        }
+        std::vector<tolcuda_gather_handle> gh(G, nullptr);
+        check(tolcuda_gather_create(h[D], B, G, D, &gh[D], nullptr), "tolcuda_gather_create");
+        for (int g = 0; g < G; g++)
+            if (g != D) check(tolcuda_gather_attach(h[g], B, G, g, D, gh[D], nullptr, &gh[g]), "tolcuda_gather_attach");
+        double *dF = nullptr, *dG = nullptr;
+        long gldF = 0, gldG = 0;
+        double gbest = 1e300;
+        for (int step = 0; step < a.steps + 1; step++) {  // one thread enqueues for every device: all calls are asynchronous
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int g = 0; g < G; g++)
+                if (g != D && dx[g]) check(tolcuda_gather_send(gh[g], dx[g], ldx, 4), "tolcuda_gather_send");
+            check(tolcuda_gather_collect(gh[D], dx[D], ldx, 4, &dF, &gldF, &dG, &gldG), "tolcuda_gather_collect");
+            for (int g = 0; g < G; g++)
+                if (g != D) check(tolcuda_synchronize(h[g]), "tolcuda_synchronize");
+            const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (step > 0) gbest = std::min(gbest, wall);
+        }
+        // rows on GPU D against the rows of the host gather, bit for bit, in slabs of 256 trajectories
+        const int slab = 256;
+        std::vector<double> tF((size_t)slab * gldF), tG((size_t)slab * gldG);
+        for (int b0 = 0; b0 < B; b0 += slab) {
+            const int nbk = std::min(slab, B - b0);
+            check(tolcuda_copy_to_host(D, tF.data(), dF + (size_t)b0 * gldF, sizeof(double) * gldF * nbk), "F rows to host");
+            check(tolcuda_copy_to_host(D, tG.data(), dG + (size_t)b0 * gldG, sizeof(double) * gldG * nbk), "G rows to host");
+            for (int b = 0; b < nbk; b++) {
+                gather_same = gather_same && !std::memcmp(tF.data() + (size_t)b * gldF, F + (size_t)(b0 + b) * ldF, sizeof(double) * neF);
+                gather_same = gather_same && !std::memcmp(tG.data() + (size_t)b * gldG, Gv + (size_t)(b0 + b) * ldG, sizeof(double) * neG);
+            }
+        }
+        std::printf("TOLBATCH: gather on GPU %d (device x -> F,G rows of all %d trajectories in its memory): best %.3f ms, "
+                    "%.4g node-evals/s; rows bit-identical to the host gather: %s\n",
+                    D, B, 1e3 * gbest, (double)B * ts / gbest, gather_same ? "yes" : "NO");
+        for (int g = 0; g < G; g++)
+            if (g != D) tolcuda_gather_close(gh[g]);
+        tolcuda_gather_close(gh[D]);
+        for (int g = 0; g < G; g++) tolcuda_device_free(g, dx[g]);
+    }
+
     if (!a.json.empty()) {
         FILE *f = std::fopen(a.json.c_str(), "w");
         if (!f) die("cannot write " + a.json);
@@ -224,5 +287,5 @@ int main(int argc, char **argv) {
         }
     for (int g = 0; g < G; g++) tolcuda_destroy(h[g]);
     tolcuda_host_free(X), tolcuda_host_free(F), tolcuda_host_free(Gv), tolcuda_host_free(S);
-    return nonfinite ? 1 : 0;
+    return (nonfinite || !gather_same) ? 1 : 0;
 }

@@ -39,6 +39,13 @@ static int cuda_fail(cudaError_t e, const char *what) {
 
 using namespace tolcuda;
 
+int tolcuda::tolcuda_copy_raw(int device, void *dst, const void *src, size_t bytes, int kind) {
+    if ((!dst || !src) && bytes) return TOLCUDA_EINVAL;
+    CU(cudaSetDevice(device));
+    CU(cudaMemcpy(dst, src, bytes, kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 // One staging lane of the host-pointer batch path: device buffers for a chunk of trajectories and
 // the stream that carries H2D -> kernel -> D2H for that chunk.
 struct BatchLane {

@@ -18,6 +18,8 @@
 namespace tolcuda {
 
 void set_error(const std::string &msg);
+// tolcuda_api.cpp: synchronous cudaMemcpy on `device`; kind 1 = host to device, 2 = device to host
+int tolcuda_copy_raw(int device, void *dst, const void *src, size_t bytes, int kind);
 
 void pattern_dims(int form, int ts, int *n, int *neF, int *neG, int *R0, int *nbG);
 void pattern_build(int form, int ts, std::vector<int> &iG, std::vector<int> &jG);

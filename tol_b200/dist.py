@@ -91,18 +91,71 @@ def eval_and_gather_device(ev, X, B, dst=0):
     return F, G
 
 
+class Gather:
+    """tolcuda_gather_* (include/tolcuda.h, gather.cpp) for one process per GPU: rank `dst` creates the gather and its
+    64-byte IPC handle travels through torch.distributed; every other rank attaches on its own device.  Collective."""
+
+    def __init__(self, ev, B, dst=0):
+        import ctypes as C
+        from . import lib as _l
+        r, w = world()
+        self.ev, self.B, self.dst, self.rank, self.world, self.L = ev, B, dst, r, w, ev.L
+        self.g = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        if r == dst:
+            _l.check(self.L.tolcuda_gather_create(ev.h, B, w, dst, C.byref(self.g), handle))
+        box = [handle.raw if r == dst else None]
+        if w > 1:
+            dist.broadcast_object_list(box, src=dst)
+        if r != dst:
+            _l.check(self.L.tolcuda_gather_attach(ev.h, B, w, r, dst, None, box[0], C.byref(self.g)))
+        base, nbytes = C.c_void_p(), C.c_size_t()
+        _l.check(self.L.tolcuda_gather_buffer(self.g, C.byref(base), C.byref(nbytes)))
+        self.ptr, self.nbytes = base.value, nbytes.value
+
+    def run(self, X, chunks=4):
+        """every rank: evaluate the local shard X into the gathering GPU's rows; returns (F [B, ldF], G [B, ldG]) as
+        CUDA tensors on rank dst (views of the gather's buffer, valid until close()), (None, None) elsewhere.  Ends
+        with a barrier: the staging region is free again when it returns."""
+        import ctypes as C
+        from . import lib as _l
+        from .evaluator import PeerBuffer
+        F = G = None
+        xp = C.c_void_p(X.data_ptr()) if X.shape[0] else None
+        if self.rank != self.dst:
+            if X.shape[0]:
+                _l.check(self.L.tolcuda_gather_send(self.g, xp, X.stride(0), int(chunks)))
+                self.ev.synchronize()
+        else:
+            Fp, Gp, ldF, ldG = C.c_void_p(), C.c_void_p(), C.c_long(), C.c_long()
+            _l.check(self.L.tolcuda_gather_collect(self.g, xp, X.stride(0) if X.shape[0] else self.ev.n, int(chunks),
+                                                   C.byref(Fp), C.byref(ldF), C.byref(Gp), C.byref(ldG)))
+            view = PeerBuffer(self.ev.device, self.ptr, self.nbytes, None)
+            F = view.tensor((Fp.value - self.ptr) // 8, self.B, ldF.value)
+            G = view.tensor((Gp.value - self.ptr) // 8, self.B, ldG.value)
+        if self.world > 1:
+            dist.barrier()
+        return F, G
+
+    def close(self):
+        if getattr(self, "g", None):
+            self.L.tolcuda_gather_close(self.g)
+            self.g = None
+
+    __del__ = close
+
+
 def eval_and_gather_peer(ev, X, B, dst=0, out=None, compact=True, chunks=4):
     """Fused evaluate + gather: rank `dst` owns one buffer holding all B rows of F and
     G; every other rank maps it over CUDA IPC (NVLink peer access) and its F/G kernel stores its shard's rows
     directly into it -- F with coalesced stores, G with the kernel's TMA bulk copies -- so the transfer happens
     record by record while the shard is being computed: no send buffer, no copy or collective afterwards.
     torch.distributed only carries the 64-byte handle and the closing barrier.
-      compact=True   the peers' G crosses NVLink as COMPACT rows (a third of the bytes: NVLink, at 0.9 TB/s per
-                     direction, is the slower side) into a staging region of the same buffer, and `dst` expands
-                     them into rows in coordinate order at HBM speed (expand_kernel.cu).  A peer's shard goes in
-                     `chunks` launches, each followed by a stream-ordered flag written into the owner's memory
-                     (tolcuda_stream_signal); the owner's stream waits on the flag (tolcuda_stream_wait) and
-                     expands that chunk while the next ones are still arriving -- no host in between
+      compact=True   the library's own protocol, tolcuda_gather_* (class Gather): the peers' G crosses NVLink as
+                     COMPACT rows (a third of the bytes: NVLink, at 0.9 TB/s per direction, is the slower side)
+                     into a staging region of the same buffer in `chunks` launches, each followed by a
+                     stream-ordered flag in the owner's memory; the owner's stream waits on the flag and expands
+                     that chunk (expand_kernel.cu) while the next ones are still arriving -- no host in between
       compact=False  the peers write full rows at their final place; nothing runs on `dst` afterwards
     Returns (F [B, ldF], G [B, ldG], buffer) as CUDA tensors on rank `dst` (rows by trajectory index, padded
     leading dimensions), (None, None, None) elsewhere.  `out`: what open_peer_buffer returned on this rank, to
@@ -110,45 +163,28 @@ def eval_and_gather_peer(ev, X, B, dst=0, out=None, compact=True, chunks=4):
     from .evaluator import padded_ld
     r, w = world()
     b0, b1 = shard_range(B, r, w)
-    ldF, ldG, ldC = padded_ld(ev.neF), padded_ld(ev.neG), padded_ld(ev.compact_len)
-    staged = compact and w > 1
-    chunks = max(1, min(int(chunks), MAX_CHUNKS))
-    nbytes = peer_buffer_bytes(ev, B, staged)
-    buf = out if out is not None else open_peer_buffer(ev, B, dst, staged)
-    assert buf.nbytes >= nbytes
-    buf.epoch = getattr(buf, "epoch", 0) + 1  # every rank calls in step, so the counters agree
-    assert not staged or buf.nbytes == nbytes, "the buffer was opened for another layout"
-    flags = buf.ptr + nbytes - FLAG_BYTES  # uint32 [w][MAX_CHUNKS], zeroed by open_peer_buffer
-
-    def pieces(q0, q1):
-        per = max(1, (q1 - q0 + chunks - 1) // chunks)
-        return [(a, min(q1, a + per)) for a in range(q0, q1, per)]
-
+    assert X.shape[0] == b1 - b0
+    if compact and w > 1:
+        g = out if out is not None else Gather(ev, B, dst)
+        assert isinstance(g, Gather), "the buffer was opened for another layout"
+        F, G = g.run(X, chunks)
+        if r != dst:
+            if out is None:
+                g.close()
+            return None, None, None
+        return F, G, g
+    ldF, ldG = padded_ld(ev.neF), padded_ld(ev.neG)
+    nbytes = peer_buffer_bytes(ev, B, False)
+    buf = out if out is not None else open_peer_buffer(ev, B, dst, False)
+    assert not isinstance(buf, Gather) and buf.nbytes >= nbytes, "the buffer was opened for another layout"
     if b1 > b0:
-        assert X.shape[0] == b1 - b0
-        if staged and r != dst:
-            for ci, (a, e) in enumerate(pieces(b0, b1)):
-                ev.eval_batch_ptrs(e - a, X[a - b0:].data_ptr(), X.stride(0), buf.ptr + 8 * a * ldF, ldF,
-                                   buf.ptr + 8 * (B * (ldF + ldG) + a * ldC), ldC, compact_rows=True, sync=False)
-                ev.stream_signal(flags + 4 * (r * MAX_CHUNKS + ci), buf.epoch)
-            ev.synchronize()
-        else:
-            ev.eval_batch_ptrs(b1 - b0, X.data_ptr(), X.stride(0), buf.ptr + 8 * b0 * ldF, ldF,
-                               buf.ptr + 8 * (B * ldF + b0 * ldG), ldG, sync=staged is False or w == 1)
+        ev.eval_batch_ptrs(b1 - b0, X.data_ptr(), X.stride(0), buf.ptr + 8 * b0 * ldF, ldF,
+                           buf.ptr + 8 * (B * ldF + b0 * ldG), ldG, sync=True)
     F = G = None
     if r == dst:
         F, G = buf.tensor(0, B, ldF), buf.tensor(B * ldF, B, ldG)
-        if staged:
-            Gc = buf.tensor(B * (ldF + ldG), B, ldC)
-            # chunk-major: the peers send concurrently, so their chunks c arrive at about the same time
-            todo = [(ci, q, a, e) for q in range(w) if q != dst
-                    for ci, (a, e) in enumerate(pieces(*shard_range(B, q, w)))]
-            for ci, q, a, e in sorted(todo):
-                ev.stream_wait(flags + 4 * (q * MAX_CHUNKS + ci), buf.epoch)
-                ev.expand_compact_device(Gc[a:e], G[a:e], sync=False)
-            ev.synchronize()
     if w > 1:
-        dist.barrier()  # every shard has landed (and been expanded) in the owner's memory; the staging region is free again
+        dist.barrier()  # every shard has landed in the owner's memory
         if r != dst:
             if out is None:
                 buf.close()
@@ -156,19 +192,17 @@ def eval_and_gather_peer(ev, X, B, dst=0, out=None, compact=True, chunks=4):
     return F, G, buf
 
 
-MAX_CHUNKS = 16
-
 
 def open_peer_buffer(ev, B, dst=0, staged=True):
-    """collective: rank `dst` allocates the gather buffer (peer_buffer_bytes) and exports it, every other rank
-    maps it on its own device; returns this rank's PeerBuffer (close() it when done)"""
+    """collective: what eval_and_gather_peer reuses over many calls -- a Gather (the library's protocol: compact rows,
+    staging region, chunk flags) when `staged` and there are peers, else a plain PeerBuffer for full rows in place
+    (rank `dst` allocates and exports it, every other rank maps it on its own device).  close() it when done."""
     from .evaluator import PeerBuffer
     r, w = world()
-    nbytes = peer_buffer_bytes(ev, B, staged and w > 1)
+    if staged and w > 1:
+        return Gather(ev, B, dst)
+    nbytes = peer_buffer_bytes(ev, B, False)
     buf = PeerBuffer.alloc(ev.device, nbytes) if r == dst else None
-    if r == dst:  # the chunk flags start at zero
-        buf.tensor((nbytes - FLAG_BYTES) // 8, 1, FLAG_BYTES // 8).zero_()
-        torch.cuda.synchronize(ev.device)
     if w > 1:
         box = [buf.handle if r == dst else None]
         dist.broadcast_object_list(box, src=dst)
@@ -178,10 +212,7 @@ def open_peer_buffer(ev, B, dst=0, staged=True):
 
 
 def peer_buffer_bytes(ev, B, staged=True):
-    """bytes of the gathering rank's buffer: F rows | G rows | (staged) compact rows of the peers"""
+    """bytes of a full-rows PeerBuffer: F rows | G rows (the staged layout is the library's, tolcuda_gather_buffer)"""
     from .evaluator import padded_ld
-    ldF, ldG, ldC = padded_ld(ev.neF), padded_ld(ev.neG), padded_ld(ev.compact_len)
-    return 8 * B * (ldF + ldG + (ldC if staged else 0)) + FLAG_BYTES
-
-
-FLAG_BYTES = 4096  # uint32 [world][MAX_CHUNKS] chunk flags behind the staging region (world <= 64)
+    assert not staged or world()[1] == 1
+    return 8 * B * (padded_ld(ev.neF) + padded_ld(ev.neG))

@@ -154,10 +154,12 @@ class PeerBuffer:
         return cls(device, p.value, nbytes, False, handle)
 
     def close(self):
+        """owner True: frees the allocation; False: unmaps the IPC mapping; None: a view of memory owned elsewhere"""
         if getattr(self, "ptr", None):
             ptr, self.ptr = self.ptr, None
             L = _l.load()
-            (L.tolcuda_device_free if self.owner else L.tolcuda_ipc_close)(int(self.device), C.c_void_p(ptr))
+            if self.owner is not None:
+                (L.tolcuda_device_free if self.owner else L.tolcuda_ipc_close)(int(self.device), C.c_void_p(ptr))
 
     __del__ = close
 

@@ -73,6 +73,14 @@ def load():
     L.tolcuda_enable_peer.argtypes = [C.c_int, C.c_int]
     L.tolcuda_stream_signal.argtypes = [vp, vp, C.c_uint]
     L.tolcuda_stream_wait.argtypes = [vp, vp, C.c_uint]
+    L.tolcuda_gather_create.argtypes = [vp, C.c_long, C.c_int, C.c_int, C.POINTER(vp), C.c_char_p]
+    L.tolcuda_gather_attach.argtypes = [vp, C.c_long, C.c_int, C.c_int, C.c_int, vp, C.c_char_p, C.POINTER(vp)]
+    L.tolcuda_gather_send.argtypes = [vp, vp, C.c_long, C.c_int]
+    L.tolcuda_gather_collect.argtypes = [vp, vp, C.c_long, C.c_int, C.POINTER(vp), C.POINTER(C.c_long), C.POINTER(vp), C.POINTER(C.c_long)]
+    L.tolcuda_gather_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.tolcuda_gather_close.argtypes = [vp]
+    L.tolcuda_copy_to_device.argtypes = [C.c_int, vp, vp, C.c_size_t]
+    L.tolcuda_copy_to_host.argtypes = [C.c_int, vp, vp, C.c_size_t]
     L.tolcuda_padded_ld.argtypes = [C.c_long]
     L.tolcuda_padded_ld.restype = C.c_long
     L.tolcuda_set_stream.argtypes = [vp, vp]
