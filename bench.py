@@ -589,8 +589,8 @@ def gather_record(torch, dist, T, ev, g, Xd, B_total, rank, world, stream):
     the gathering rank's host (perf_counter around synchronised calls, max over ranks); bit-identity of the two
     results is checked on the full arrays."""
     import tol_b200.dist as D
-    ev.use_own_stream()
     torch.cuda.set_stream(torch.cuda.default_stream())
+    ev.follow_torch_stream()  # the gathers allocate and fill through torch: one stream orders everything
     reps = 5
     buf = D.open_peer_buffer(ev, B_total, 0, True)
     out = {}

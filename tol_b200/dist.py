@@ -65,8 +65,12 @@ def eval_and_gather_device(ev, X, B, dst=0):
     nb = X.shape[0]
     per = (B + w - 1) // w
     Lc = ev.compact_len
-    Fl = torch.zeros(per, ev.neF, dtype=torch.float64, device=X.device)
-    Gl = torch.zeros(per, Lc, dtype=torch.float64, device=X.device)
+    # the kernel runs on the stream torch has queued these allocations (and the tail fill) on: Evaluator follows
+    # torch's current stream unless the caller pinned another one, in which case the caller orders the two
+    Fl = torch.empty(per, ev.neF, dtype=torch.float64, device=X.device)
+    Gl = torch.empty(per, Lc, dtype=torch.float64, device=X.device)
+    Fl[nb:].zero_()  # rows of the padded shard no trajectory owns
+    Gl[nb:].zero_()
     if nb:
         ev.eval_batch_device(X, Fl[:nb], Gl[:nb], compact_rows=True)
     if w == 1:
@@ -79,7 +83,7 @@ def eval_and_gather_device(ev, X, B, dst=0):
     dist.gather(Gl, Gp, dst=dst)
     if r != dst:
         return None, None
-    torch.cuda.current_stream().synchronize()  # the gathers ran on torch's stream, the expansion runs on the context's
+    torch.cuda.current_stream().synchronize()  # the gathers were issued from torch's stream; the expansions below are ordered after them
     F = torch.empty(B, ev.neF, dtype=torch.float64, device=X.device)
     G = torch.empty(B, ev.neG, dtype=torch.float64, device=X.device)
     for q in range(w):
@@ -121,6 +125,7 @@ class Gather:
         from . import lib as _l
         from .evaluator import PeerBuffer
         F = G = None
+        self.ev._follow_torch(X)  # what torch has queued on X (and, on the owner, on the buffer) comes first
         xp = C.c_void_p(X.data_ptr()) if X.shape[0] else None
         if self.rank != self.dst:
             if X.shape[0]:

@@ -378,6 +378,10 @@ class Evaluator:
         self._stream_pinned = True
         _l.check(self.L.tolcuda_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
+    def follow_torch_stream(self):
+        """back to the default: tensor calls run on torch's current stream"""
+        self._stream_pinned = False
+
     def use_own_stream(self):
         self._stream_pinned = True
         _l.check(self.L.tolcuda_use_own_stream(self.h))
