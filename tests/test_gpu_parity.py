@@ -530,6 +530,51 @@ def test_reference_driver_with_libtolcuda_dropped_in(args, fixture, tmp_path):
     assert_parity(np.array(docs["cuda"]["trajectory"]["x"]), np.array(docs["ref"]["trajectory"]["x"]), "x*")
 
 
+@pytest.mark.parametrize("args,fixture", [
+    (["0", "0", "70", "0", "-100", "0", "100", "tempest", "S10"], "S10_tempest_ts100"),
+    (["0", "0", "70", "400", "0", "0", "0", "skywalker", "G7"], "G7_skywalker_ts100")])
+def test_long_callback_sequence_does_not_drift(args, fixture, tmp_path):
+    """BASELINE.json configs[4] cannot run without the SNOPT library; what CAN be bounded is drift: the same two
+    drivers (the reference's own DefineFG.o / libtolcuda's DEFINEGusrfg_) under the SNOPT stand-in for 240 calls of
+    mixed kind (F+G, F only, G only), every iterate fed by the previous call's G.  Iterates, F and G of the two runs
+    must stay within the parity tolerance on EVERY call -- a last-ulp difference that fed on itself would show."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "tol_dropin_ref")
+    cuda_exe = os.path.join(ROOT, "oracle", "_ref", "tol_dropin_cuda")
+    root = os.path.join(ROOT, "oracle", "_ref", "params") + "/"
+    if not (os.path.exists(ref_exe) and os.path.exists(cuda_exe) and os.path.isdir(root)):
+        pytest.skip("oracle/_ref drop-in binaries are not built (make -C oracle ref, build container only)")
+    g = load_golden(fixture)
+    steps, logs = 239, {}
+    for tag, exe in (("ref", ref_exe), ("cuda", cuda_exe)):
+        wd = tmp_path / tag
+        wd.mkdir()
+        log = str(wd / "calls.bin")
+        r = subprocess.run([exe] + args + [root], cwd=wd, env=dict(os.environ, SNMOCK_LOG=log, SNMOCK_STEPS=str(steps)),
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        logs[tag] = _read_snmock_log(log)[3]
+        os.remove(log)
+    cref, ccuda = logs["ref"], logs["cuda"]
+    assert len(cref) == len(ccuda) == steps + 1
+    mask = np.ones(int(g["neG"]), bool)
+    mask[g["ub_mask"]] = False
+    kinds = set()
+    moved = 0.0
+    for k, (a, b) in enumerate(zip(cref, ccuda)):
+        assert a[:3] == b[:3]
+        kinds.add(a[1:3])
+        assert_parity(b[3], a[3], "call %d x" % k)
+        if a[1]:
+            assert_parity(b[4], a[4], "call %d F" % k)
+        if a[2]:
+            assert_parity(b[5][mask], a[5][mask], "call %d G" % k)
+        moved = max(moved, float(np.abs(a[3] - cref[0][3]).max()))
+    assert kinds == {(1, 1), (1, 0), (0, 1)} and moved > 1e-3  # all three kinds of call; the iterates did move
+
+
 @pytest.mark.parametrize("name", ["S10_tempest_ts100", "G7_skywalker_ts100"])
 def test_degenerate_inputs_are_non_finite_where_the_reference_is(name, oracle_built):
     """Inputs outside the bounds SNOPT keeps (Va = 0, cos(gamma) = 0, a node exactly on the loiter centre):
