@@ -68,3 +68,29 @@ def test_shard_ranges_cover_the_batch_exactly():
             assert r[0][0] == 0 and r[-1][1] == B
             assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
             assert all(b1 >= b0 for b0, b1 in r)
+
+
+def test_bench_reference_arm_prints_the_same_config_as_the_gpu_arm(oracle_built):
+    """bench.py --impl reference (CPU only: the reference's own path on the host cores, a bounded sample of the same
+    batch) prints the line of the contract -- same metric, unit and CONFIG as the GPU arm, impl = reference, a
+    cpu_baseline describing the run, e2e with zero copies -- and, launched as ranks 0 and 1, only rank 0 works."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1",
+           "--cpu-budget", "4", "--batch", "2048"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, RANK="0", WORLD_SIZE="2"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == bench.METRIC and line["unit"] == bench.UNIT
+    assert line["config"] == bench.config_of("S10_tempest_ts200_B65536", 2048)  # what run_ours prints as `config`
+    assert line["higher_is_better"] is True and line["scaling"] == "strong" and line["n_gpus"] == 2 and line["dtype"] == "f64"
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] > 0
+    assert line["sample"]["sample_of"] == 2048 and 0 < line["sample"]["rows_per_step"] <= 2048
+    assert line["e2e"] == {"value": line["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=60, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r.returncode == 0 and r.stdout.strip() == ""
