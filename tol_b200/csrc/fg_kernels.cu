@@ -92,6 +92,8 @@ constexpr int MODE_PLAIN = 0, MODE_SUMMARY = 1, MODE_COMPACT = 2;
 // receives y, the G pointer holds d), MODE_VJP  z = J(x)^T lambda  (the F pointer holds lambda, the G pointer receives z)
 constexpr int MODE_JVP = 3, MODE_VJP = 4;
 __host__ __device__ constexpr bool mode_is_op(int mode) { return mode == MODE_JVP || mode == MODE_VJP; }
+// the flavours that assemble whole records in the warp's record slots (the others use the tile as plain staging)
+__host__ __device__ constexpr bool mode_has_records(int mode) { return mode == MODE_PLAIN || mode == MODE_SUMMARY; }
 
 // Kernel experiment switches (bits 2.. of the kernels' needG argument: 4 = stage but do not store G, 8 = no
 // trigonometry, 16 = no Jacobian arithmetic) exist only in the experiments build (make exp -> libtolcuda_exp.so,
@@ -691,6 +693,14 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
     v[29] = -dphi;  // F7 :1172
     v[30] = -dCL;   // F8 :1184
     }
+#ifndef TOLCUDA_OP_NOPIN
+    if (OP) {
+        // the 31 entries meet in registers before the products consume them: left free, ptxas interleaves their
+        // arithmetic with the dot products and spills at the 128-register cap
+#pragma unroll
+        for (int i = 0; i < NVAR; i++) asm volatile("" : "+d"(v[i]));
+    }
+#endif
 
     if (MODE == MODE_JVP) {
         // y = J d for this warp's rows: the window's 8 defect rows (src/problem.cpp:1074-1192 entries times the
@@ -1105,9 +1115,11 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int nrun, int per_arg, const do
     }
     // alignment of this warp's records in the run's first trajectory (tile_eval re-initialises the slots if a
     // later trajectory's differs: odd leading dimension)
-    int tile_mis = (int)(reinterpret_cast<uintptr_t>(G + b0 * ldG + c.R0 + (size_t)REC * k0) >> 3) & 1;
-    if (UNIT != NPP) tile_mis = 0;
-    if (needG && !OP) tile_init(tile, lane, tile_mis);
+    int tile_mis = 0;
+    if (mode_has_records(MODE)) {
+        if (UNIT == NPP) tile_mis = (int)(reinterpret_cast<uintptr_t>(G + b0 * ldG + c.R0 + (size_t)REC * k0) >> 3) & 1;
+        if (needG) tile_init(tile, lane, tile_mis);
+    }
     if (tid < MAXPER) arrivals[tid] = 0;
     __syncthreads();
 #pragma unroll 1
@@ -1135,7 +1147,7 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int nrun, int per_arg, const do
             __syncwarp();
         }
         tile_eval<FORM, WIND, MODE>(c, wsm + slot * SX_LEN, tile, tile_s, dt, k0, nk, lane, Fb, Gb, needF, needG, tsum,
-                                    t == 0 && (flow & FLOW_WAIT), tile_mis, OP ? tile : nullptr);
+                                    !OP && t == 0 && (flow & FLOW_WAIT), tile_mis, OP ? tile : nullptr);
         __syncwarp();
         const double sumT = warp_sum(tsum.sumT);
         const double sump = FORM == TOLCUDA_FORM_S10 ? warp_sum(tsum.sump) : 0.0;
@@ -1212,8 +1224,11 @@ fg_long_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, 
         n0 = __ldg(xb + 1 + lane);
         ne = __ldg(xb + (size_t)PX * ts + 1 + lane);
     }
-    int tile_mis = (UNIT == NPP) ? (int)(reinterpret_cast<uintptr_t>(Gb + c.R0) >> 3) & 1 : 0;  // REC*k0 is even
-    if (needG && !OP) tile_init(tile, lane, tile_mis);
+    int tile_mis = 0;
+    if (mode_has_records(MODE)) {
+        if (UNIT == NPP) tile_mis = (int)(reinterpret_cast<uintptr_t>(Gb + c.R0) >> 3) & 1;  // REC*k0 is even
+        if (needG) tile_init(tile, lane, tile_mis);
+    }
     if (tid == 0) arrivals = 0;
     __syncthreads();
     double accT = 0.0, accp = 0.0, accm = 0.0, accq = 0.0;
@@ -1232,7 +1247,7 @@ fg_long_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, 
             __syncwarp();
         }
         tile_eval<FORM, WIND, MODE>(c, wsm + slot * SX_LEN, tile, tile_s, dt, 32 * j, min(32, ts - 32 * j), lane, Fb, Gb,
-                                    needF, needG, tsum, j == warp && (flow & FLOW_WAIT), tile_mis, OP ? tile : nullptr);
+                                    needF, needG, tsum, !OP && j == warp && (flow & FLOW_WAIT), tile_mis, OP ? tile : nullptr);
         __syncwarp();
         accT += tsum.sumT;
         accp += tsum.sump;
