@@ -252,7 +252,8 @@ int tolcuda_set_host_threads(tolcuda_handle h, int threads);
  *                    host memory; 0: staged cudaMemcpyAsync copies
  *   "compact_host"   1 (default): the host-pointer batch path moves compact G rows across PCIe and expands them on
  *                    host threads; 0: full rows cross PCIe (as with TOLCUDA_FULL_G_COPY)
- *   "chunk_mb"       host-pointer batch path: device megabytes per pipeline lane (default 32)
+ *   "chunk_mb"       host-pointer batch path: upper limit of the device megabytes per pipeline lane (default 32;
+ *                    a call is cut into ~160 chunks of at least 1 MB, so smaller batches use smaller chunks)
  * Returns TOLCUDA_EINVAL for an unknown name or a value out of range. */
 int tolcuda_set_option(tolcuda_handle h, const char *name, long value);
 

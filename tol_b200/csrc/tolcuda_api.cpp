@@ -692,7 +692,12 @@ int tolcuda_eval_batch_summary(tolcuda_handle h, int B, const double *x, long ld
     const long dldG = tolcuda_padded_ld(dev_compact ? lenGc : (long)c.neG);
     const long rowG = dev_compact ? lenGc : (long)c.neG;  // doubles of a G row that cross PCIe
     const size_t per_traj = sizeof(double) * (size_t)(dldx + dldF + dldG);
-    const size_t budget = (size_t)h->chunk_mb << 20;  // device bytes per lane
+    // device bytes per lane: at most chunk_mb, and small enough for ~160 chunks per call (never below 1 MB) -- the
+    // first chunk's copies and kernel and the last chunk's expansion are not overlapped with anything, which costs
+    // 10-15 % of a call made of 21 chunks (8,192 rows, one GPU's shard of 8) and nothing at 160
+    // (tools/e2e_sweep.py, profiles/r2_e2e_sweep_8gpu.jsonl)
+    const size_t cap = (size_t)h->chunk_mb << 20;
+    const size_t budget = std::min(cap, std::max<size_t>((size_t)1 << 20, per_traj * (size_t)B / 160));
     int chunk = (int)std::max<size_t>(1, budget / per_traj);
     chunk = std::min(chunk, B);
     if (B > chunk && B < NLANES * chunk) chunk = (B + NLANES - 1) / NLANES;
