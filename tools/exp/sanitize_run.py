@@ -11,7 +11,8 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import tol_b200 as T  # noqa: E402
 
-for name in ("S10_tempest_ts200", "G7_skywalker_ts100", "S10_tempest_ts100_wind3", "S10_tempest_ts1"):
+for name in ("S10_tempest_ts200", "G7_skywalker_ts100", "S10_tempest_ts100_wind3", "S10_tempest_ts1", "S10_tempesteric_ts33",
+             "G7_tempestwences_ts45_gains", "S10_skywalker_ts7_gains"):  # odd ts: record slots shifted by one double
     g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
     for kernel, per in ((0, None), (0, 1), (0, 3), (2, None)):
         ev = T.Evaluator.from_golden(g, options={"kernel": kernel, "per": per or 0})
@@ -36,5 +37,18 @@ for name in ("S10_tempest_ts200", "G7_skywalker_ts100", "S10_tempest_ts100_wind3
         assert torch.allclose(lhs, rhs, rtol=1e-9, atol=1e-9)
         f1, g1 = ev.eval(X[0])
         assert np.array_equal(G, G2) and np.array_equal(f1, F[0]) and np.array_equal(Gd.cpu().numpy()[:, :ev.neG], G)
+        # launch shapes with a single-trajectory tail, and programmatic dependent launches (both forms)
+        ld = T.evaluator.padded_ld(ev.neG)
+        outs = [(torch.empty(B, ev.neF, dtype=torch.float64, device="cuda"), torch.empty(B, ld, dtype=torch.float64, device="cuda"))
+                for _ in range(2)]
+        for p2, tail in ((2, 1), (2, 64), (3, 2)):
+            ev.set_option("per", p2)
+            ev.set_option("tail_x4", tail)
+            for ov in (0, 1, 2):
+                for i in range(4):
+                    ev.eval_batch_device(Xd, outs[i & 1][0], outs[i & 1][1], sync=False, overlap=ov)
+                ev.synchronize()
+                for Fo, Go in outs:
+                    assert np.array_equal(Fo.cpu().numpy(), F) and np.array_equal(Go.cpu().numpy()[:, :ev.neG], G)
         ev.close()
 print("sanitize_run ok")
