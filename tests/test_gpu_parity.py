@@ -410,6 +410,20 @@ def test_long_trajectories(mission, ts, oracle_built):
     ev.close()
 
 
+def _assert_parity_F_with_cancellation_bound(F, Fr, x, ts, what):
+    """F against Fr at the state x: every entry within 1e-14 + 1e-12*|ref|, the defect rows x_{k+1} - xdot*dt - x_k
+    within that plus ONE ULP of the larger of their two states (the documented limit of the absolute floor, see
+    test_defect_cancellation_at_the_exact_initial_guess)"""
+    nodes = x[1:].reshape(ts + 1, 11)
+    scale = np.maximum(np.abs(nodes[:-1, :8]), np.abs(nodes[1:, :8])).ravel()  # per defect: its two states
+    err = np.abs(F - Fr)
+    d = slice(1, 1 + 8 * ts)
+    bad = err[d] > 1e-14 + 1e-12 * np.abs(Fr[d]) + np.spacing(scale)
+    assert not bad.any(), "%s: defect rows %s outside 1e-14 + 1e-12*|ref| + ulp(state): err %s" % (
+        what, np.where(bad)[0][:6], err[d][bad][:6])
+    assert_parity(np.delete(F, np.arange(1, 1 + 8 * ts)), np.delete(Fr, np.arange(1, 1 + 8 * ts)), what + " F[0], boundary")
+
+
 def test_defect_cancellation_at_the_exact_initial_guess(oracle_built):
     """Documented limit of the 1e-14 absolute floor.  At the reference's own x0 with a fine grid the
     defects x_{k+1} - xdot*dt - x_k are ~1e-3 while the positions are ~1e2: the reference's expression
@@ -542,7 +556,8 @@ def test_long_callback_sequence_does_not_drift(args, fixture, tmp_path, oracle_b
       * on every call the CUDA run's F and G are within the tolerance of the reference arithmetic AT THE CUDA RUN'S
         OWN x (the oracle port, pinned bit for bit to the reference): F and G of the two runs cannot be compared
         directly once the iterates differ in the last bit -- a defect row is a difference of two x entries of size
-        100, so one ulp of x is 1.4e-14 of F;
+        100, so one ulp of x is 1.4e-14 of F.  The defect rows carry the documented cancellation allowance of one
+        ulp of their states (test_defect_cancellation_at_the_exact_initial_guess);
       * the reference run's F and G are the port's at the reference run's x, bit for bit (the pin, once more)."""
     import os
     import subprocess
@@ -576,8 +591,8 @@ def test_long_callback_sequence_does_not_drift(args, fixture, tmp_path, oracle_b
         assert_parity(b[3], a[3], "call %d x" % k)
         Fp, Gp = port.eval(b[3])
         Fr, Gr = port.eval(a[3])
-        if a[1]:
-            assert_parity(b[4], Fp, "call %d F" % k)
+        if a[1]:  # the iterates sit near x0, where the defects are ~1e-2 of positions ~1e2: cancellation bound
+            _assert_parity_F_with_cancellation_bound(b[4], Fp, b[3], int(g["ts"]), "call %d F" % k)
             assert np.array_equal(a[4], Fr)
         if a[2]:
             assert_parity(b[5][mask], Gp[mask], "call %d G" % k)
