@@ -1070,7 +1070,7 @@ __device__ __forceinline__ void op_epilogue(const FgConst &c, const int lane, co
 // t+2 as soon as trajectory t has left its buffer, so from the second trajectory on neither the CTA launch nor
 // the x load is on the critical path, and the record slots' constants are written once per run.  Measured
 // (S10 ts=200, B=65,536): per = 1 2.174 ms, 2 2.068, 3 2.098, 4 2.113, 6 2.156, 8 2.185 (longer runs leave a
-// longer tail at the end of the grid); per = 2 is the default (TOLCUDA_PER).
+// longer tail at the end of the grid); per = 2 is the default (tolcuda_set_option "per").
 constexpr int MAXPER = 4;
 template <int FORM, int WIND, int MAXT, int MINB, int MODE, bool LOOP>
 __global__ void __launch_bounds__(MAXT, MINB)
@@ -1191,7 +1191,7 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int nrun, int per_arg, const do
 // Up to 8 warps (the host picks the count that balances the tiles); warp w walks tiles w, w+W, w+2W, ... of the trajectory, keeping its share of the cost
 // sums in registers, while the slice of its next tile is already in flight into the other slice buffer; the sums
 // cross warps once per trajectory as in kernel A.  Serves trajectories longer than 256 windows (and any
-// trajectory with TOLCUDA_KERNEL=2).  All warps of a CTA write the same G row, as in kernel A: the earlier
+// trajectory with tolcuda_set_option(h, "kernel", 2)).  All warps of a CTA write the same G row, as in kernel A: the earlier
 // persistent-warp kernel (one whole trajectory per warp, 16 x 148 rows being written at a time) reached 0.82 of
 // the roofline on S10 ts=200 where kernel A reaches 0.98.
 constexpr int LWARPS = 8;
@@ -1345,7 +1345,7 @@ cudaError_t launch_long(const FgLaunch &L) {
     const int nt = (L.c->ts + 31) / 32;
     const int rounds = (nt + LWARPS - 1) / LWARPS;
     int nthr = 32 * ((nt + rounds - 1) / rounds);
-    if (L.lwarps > 0) nthr = 32 * (L.lwarps < nt ? L.lwarps : nt);  // experiments (TOLCUDA_LWARPS)
+    if (L.lwarps > 0) nthr = 32 * (L.lwarps < nt ? L.lwarps : nt);  // tolcuda_set_option "lwarps"
     const size_t smem = sizeof(double) * (size_t)(nthr / 32) * WARP_SMEM_B;
     static std::atomic<size_t> configured[MAX_DEVICES];  // per device, see launch_cta_as
     std::atomic<size_t> &done = configured[L.device & (MAX_DEVICES - 1)];

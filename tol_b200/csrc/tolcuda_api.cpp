@@ -595,7 +595,7 @@ int tolcuda_eval(tolcuda_handle h, const double *x, int needF, double *F, int ne
     cudaStream_t st = h->stream;
     std::memcpy(h->h_one + h->ox, x, sizeof(double) * c.n);
     // G crosses PCIe as a compact row (a third of the bytes) and is expanded straight into the caller's array
-    // with ordinary stores -- SNOPT reads it next (TOLCUDA_COMPACT=0: the full row is copied instead)
+    // with ordinary stores -- SNOPT reads it next (option "compact_host" = 0: the full row is copied instead)
     const int compact = needG > 0 && h->compact_host;
     const long lenG = compact ? compact_len(c.form, c.ts) : (long)c.neG;
     if (h->zero_copy) {
@@ -684,7 +684,7 @@ int tolcuda_eval_batch_summary(tolcuda_handle h, int B, const double *x, long ld
     // H2D(x) -> kernel -> D2H(F, G) for its chunk, so one lane's copies overlap another's kernel.
     // G normally crosses PCIe as compact rows (31 of a window's 104 values, compact.cpp) into the lane's
     // pinned landing area and is expanded from there into the caller's G by the host thread pool while
-    // the next lanes are in flight; TOLCUDA_FULL_G_COPY (or TOLCUDA_COMPACT=0, or a summary request)
+    // the next lanes are in flight; TOLCUDA_FULL_G_COPY (or option "compact_host" = 0, or a summary request)
     // copies full rows straight into the caller's G instead.
     const bool via_compact = needG && !compact_rows && !summary && h->compact_host && !(flags & TOLCUDA_FULL_G_COPY);
     const bool dev_compact = via_compact || compact_rows;  // layout of the lane's d_G
