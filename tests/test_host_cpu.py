@@ -87,6 +87,25 @@ def test_no_cpu_fallback_without_a_device():
         T.Evaluator.from_golden(g)
 
 
+def test_gather_and_option_entry_points_refuse_bad_arguments_without_touching_a_device():
+    """tolcuda_gather_* / tolcuda_set_option / the copy wrappers (include/tolcuda.h) validate before they reach CUDA:
+    null handles and null pointers come back as TOLCUDA_EINVAL on a box with no GPU, closing nothing is a no-op"""
+    import ctypes as C
+    L = T.load()
+    out = C.c_void_p()
+    hd = C.create_string_buffer(64)
+    assert L.tolcuda_gather_create(None, 16, 2, 0, C.byref(out), hd) == -1 and not out.value
+    assert L.tolcuda_gather_create(None, 16, 2, 0, None, hd) == -1
+    assert L.tolcuda_gather_attach(None, 16, 2, 1, 0, None, hd.raw, C.byref(out)) == -1 and not out.value
+    assert L.tolcuda_gather_attach(None, 16, 2, 1, 0, None, None, C.byref(out)) == -1   # neither an owner nor a handle
+    assert L.tolcuda_gather_send(None, None, 0, 4) == -1
+    assert L.tolcuda_gather_collect(None, None, 0, 4, None, None, None, None) == -1
+    assert L.tolcuda_gather_buffer(None, None, None) == -1
+    assert L.tolcuda_gather_close(None) == 0
+    assert L.tolcuda_set_option(None, b"per", 1) == -1
+    assert L.tolcuda_copy_to_device(0, None, None, 8) == -1 and L.tolcuda_copy_to_host(0, None, None, 8) == -1
+
+
 def test_synthetic_batch_is_shard_invariant():
     g = load_golden("G7_skywalker_ts2")
     x0 = g["x"][0]
