@@ -203,6 +203,36 @@ def cpu_single_core(fixture, seed0, seconds=4.0):
     return out
 
 
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return None
+
+
+def port_single_core(fixture, seed0, seconds=2.0):
+    """for context: the repo's own non-redundant CPU restatement, oracle/fg_oracle.c, one core"""
+    import portclient as P
+    import tol_b200.synth as synth
+    if not P.available():
+        return None
+    g = golden(fixture)
+    p = _make_problem(fixture, False)
+    X = synth.batch(g["x"][0], seed0, 0, 64)
+    F, G = np.empty((64, p.neF)), np.empty((64, p.neG))
+    p.eval_many(X, F, G)
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        p.eval_many(X, F, G)
+        n += 64
+    dt = time.perf_counter() - t0
+    return {"value": n * int(g["ts"]) / dt, "unit": UNIT, "cores": 1, "ms_per_call": 1e3 * dt / n,
+            "what": "oracle/fg_oracle.c (plain-C restatement, every sub-expression once per node), not the baseline"}
+
+
 def run_reference_arm(args, wl_name):
     fixture, seed0, B_total = WORKLOADS[wl_name]
     B_total = args.batch or B_total
@@ -228,7 +258,8 @@ def run_reference_arm(args, wl_name):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": config_of(wl_name, B_total),
         "sample": {"sample_of": B_total, "rows_per_step": arm.rows, "what": arm.sample()},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.sample()},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.sample(),
+                         "cpu_model": cpu_model()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -307,14 +338,17 @@ def ncu_traffic(wl_name, alg_bytes, sass_hash):
     try:
         t = json.load(open(p)).get(wl_name)
     except (OSError, ValueError):
-        return None, "no record"
+        return None, "no record", None
     if not t:
-        return None, "no record for this workload"
+        return None, "no record for this workload", None
     if sass_hash is None:
-        return None, "cuobjdump unavailable: the record (kernel %s) cannot be tied to the loaded kernel" % t.get("kernel_sass_sha256_16")
+        return None, "cuobjdump unavailable: the record (kernel %s) cannot be tied to the loaded kernel" % t.get("kernel_sass_sha256_16"), None
     if t.get("kernel_sass_sha256_16") != sass_hash:
-        return None, "stale: record was captured for kernel %s, this library's kernel is %s" % (t.get("kernel_sass_sha256_16"), sass_hash)
-    return t["ratio"] * alg_bytes, "profiles/roofline_traffic.json (%s; ratio to algorithmic bytes applied; kernel SASS %s)" % (t.get("source"), sass_hash)
+        return None, "stale: record was captured for kernel %s, this library's kernel is %s" % (t.get("kernel_sass_sha256_16"), sass_hash), None
+    ncu = {k: t[k] for k in ("fp64_pipe_pct", "issue_active_pct", "dram_cycles_active_pct", "duration_under_ncu_ms", "captured_B") if k in t}
+    if ncu:  # secondary bound: FP64 pipe utilisation of the same capture, and the DFMA peak measured with tools/exp/fp64peak.cu
+        ncu["fp64_dfma_peak_tflops"] = {"measured": 33.9, "nominal": 37.2, "source": "tools/exp/fp64peak.cu, profiles/r1_history.md"}
+    return t["ratio"] * alg_bytes, "profiles/roofline_traffic.json (%s; ratio to algorithmic bytes applied; kernel SASS %s)" % (t.get("source"), sass_hash), ncu
 
 
 def host_ceiling(world, threads_total):
@@ -499,7 +533,7 @@ def run_ours(args, wl_name):
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
     sass_hash = kernel_sass_hash(str(g["mission"]), int(g["wind_model"]), ts) if rank == 0 else None
-    traffic, traffic_src = ncu_traffic(wl_name, alg_bytes, sass_hash) if rank == 0 else (None, None)
+    traffic, traffic_src, ncu_rec = ncu_traffic(wl_name, alg_bytes, sass_hash) if rank == 0 else (None, None, None)
     clen = padded_ld(ev.compact_len)
     h2d, d2h, fill = 8.0 * n * B_total, 8.0 * (neF + clen) * B_total, 8.0 * neG * B_total
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -543,7 +577,8 @@ def run_ours(args, wl_name):
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "kernel": "fg_cta_kernel<%s, wind %d, PLAIN, runs of 2 trajectories per CTA + single-trajectory tail>" % (str(g["mission"]), int(g["wind_model"])),
                      "kernel_sass_sha256_16": sass_hash, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
-                     "frac_serial": alg_bytes / (ms_serial * 1e-3) / 1e9 / peak},
+                     "frac_serial": alg_bytes / (ms_serial * 1e-3) / 1e9 / peak, "frac_of_nominal_8000_GBps": achieved / 8000.0,
+                     "ncu": ncu_rec},
         "clocks": clocks,
     }
 
@@ -583,11 +618,12 @@ def run_ours(args, wl_name):
             arm.step()
             v, wall = arm.step()
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
-                                    "sample": arm.sample(), "seconds": wall}
+                                    "sample": arm.sample(), "seconds": wall, "cpu_model": cpu_model()}
             arm.close()
             single = cpu_single_core(fixture, seed0)
             if single:
                 line["cpu_baseline"].update(single)
+            line["cpu_baseline"]["port_1core"] = port_single_core(fixture, seed0)
     if world > 1:
         dist.barrier()
     if rank == 0:
