@@ -361,6 +361,14 @@ def test_tolbatch_driver_end_to_end(tmp_path):
         assert sm["summary_only"] is True and sm["nonfinite"] == 0
         for a, b in zip(sm["trajectories"], d["trajectories"]):
             assert a["objective"] == b["objective"] and a["max_abs_defect"] == b["max_abs_defect"]
+        # --host-path full / auto: the same trajectories, bit for bit (the path only decides how G crosses PCIe)
+        for hp in ("full", "auto"):
+            js = str(tmp_path / ("hp_%s.json" % hp))
+            r = subprocess.run([exe] + args + ["--root", root, "--batch", "300", "--steps", "1", "--json", js, "--host-path", hp],
+                               capture_output=True, text=True, timeout=180)
+            assert r.returncode == 0, r.stdout + r.stderr
+            assert json.load(open(js))["trajectories"] == d["trajectories"]
+            assert (hp != "auto") or "host path calibration" in r.stdout
         # the same batch gathered on ONE GPU by the shards' own kernels (tolcuda_gather_*, the C form of
         # tol_b200.dist.eval_and_gather_peer): on every GPU count present, every choice of the gathering GPU, the
         # rows in its memory are bit for bit the rows of the host gather (tolbatch compares them and says so)

@@ -14,6 +14,10 @@
 //                                             summary the kernels compute on the fly comes back
 //                                             (tolcuda_eval_batch_summary without F or G: objective, worst defect,
 //                                             worst boundary violation), no F/G rows on the host
+//            [--host-path compact|full|auto]  how G reaches the host rows: compact rows across PCIe + expansion by host
+//                                             threads (default), every G value across PCIe, or whichever of the two
+//                                             a calibration call of each finds faster on this box (the answer depends
+//                                             on the host: its DMA ingest rate against its cores' store rate)
 //            [--gather-gpu D]                 after the host gather: the same batch once more with every GPU's shard
 //                                             written straight into GPU D's memory by the shards' own kernels
 //                                             (tolcuda_gather_*: NVLink peer stores, no host in between), timed, and
@@ -34,7 +38,7 @@ namespace {
 
 struct Args {
     double enu[3] = {0, 0, 0}, goal[4] = {0, 0, 0, 0};
-    std::string aircraft, mission, root = "./", xfile, json, results;
+    std::string aircraft, mission, root = "./", xfile, json, results, host_path = "compact";
     int ts = 0, batch = 4096, gpus = 0, steps = 3, nresults = 4, gather_gpu = -1;
     bool summary_only = false;
     uint64_t seed = 1;
@@ -91,6 +95,7 @@ Args parse(int argc, char **argv) {
         else if (k == "--nresults") a.nresults = std::atoi(val());
         else if (k == "--summary-only") a.summary_only = true;
         else if (k == "--gather-gpu") a.gather_gpu = std::atoi(val());
+        else if (k == "--host-path") a.host_path = val();
         else if (k == "--perturb") {
             if (std::sscanf(val(), "%lf,%lf", &a.rel, &a.abs_) != 2) die("--perturb wants REL,ABS");
         } else die("unknown option " + k);
@@ -101,6 +106,7 @@ Args parse(int argc, char **argv) {
     if (a.nresults < 0) die("--nresults must not be negative");
     if (a.gpus < 0) die("--gpus must not be negative");
     if (a.ts < 0) die("--ts must not be negative");
+    if (a.host_path != "compact" && a.host_path != "full" && a.host_path != "auto") die("--host-path wants compact, full or auto");
     if (a.gather_gpu >= 0 && a.summary_only) die("--gather-gpu gathers F and G rows: not available with --summary-only");
     return a;
 }
@@ -160,7 +166,17 @@ int main(int argc, char **argv) {
     // evaluate: one host thread per device, contiguous block of trajectory indices each, no collective
     std::vector<double> secs(G, 0.0);
     double best = 1e300;
-    for (int step = 0; step < a.steps; step++) {
+    int path_flag = a.host_path == "full" ? TOLCUDA_FULL_G_COPY : 0;
+    double cal[2] = {0.0, 0.0};
+    // --host-path auto: two untimed calls of each path (the first one allocates), the faster second call wins
+    const int ncal = (a.host_path == "auto" && !a.summary_only) ? 4 : 0;
+    for (int step = -ncal; step < a.steps; step++) {
+        if (step < 0) path_flag = ((step + ncal) / 2) ? TOLCUDA_FULL_G_COPY : 0;
+        if (step == 0 && ncal) {
+            path_flag = cal[1] < 0.95 * cal[0] ? TOLCUDA_FULL_G_COPY : 0;
+            std::printf("TOLBATCH: host path calibration: compact rows %.3f ms, full rows %.3f ms -> %s\n", 1e3 * cal[0],
+                        1e3 * cal[1], path_flag ? "full rows" : "compact rows");
+        }
         std::vector<std::thread> th;
         const auto t0 = std::chrono::steady_clock::now();
         for (int g = 0; g < G; g++)
@@ -173,12 +189,16 @@ int main(int argc, char **argv) {
                           "tolcuda_eval_batch_summary");
                 else if (b1 > b0)
                     check(tolcuda_eval_batch(h[g], b1 - b0, X + (size_t)b0 * ldx, ldx, F + (size_t)b0 * ldF, ldF,
-                                             Gv + (size_t)b0 * ldG, ldG, TOLCUDA_NEED_F | TOLCUDA_NEED_G | TOLCUDA_HOST_PTRS),
+                                             Gv + (size_t)b0 * ldG, ldG, TOLCUDA_NEED_F | TOLCUDA_NEED_G | TOLCUDA_HOST_PTRS | path_flag),
                           "tolcuda_eval_batch");
                 secs[g] = std::chrono::duration<double>(std::chrono::steady_clock::now() - s0).count();
             });
         for (auto &t : th) t.join();
         const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (step < 0) {
+            cal[(step + ncal) / 2] = wall;  // the second call of a path overwrites the first
+            continue;
+        }
         best = std::min(best, wall);
         std::printf("TOLBATCH: step %d: %.3f ms wall, %.4g node-evals/s end to end (host x -> host %s)\n", step,
                     1e3 * wall, (double)B * ts / wall, a.summary_only ? "summary" : "F,G");
