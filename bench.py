@@ -364,22 +364,24 @@ def host_ceiling(world, threads_total):
         return None
 
 
-def e2e_ceilings(hc, h2d, d2h_c, d2h_f, fill, staged):
-    """Seconds per step the host side needs AT LEAST, per path, as the slowest of three resources (rates from
-    tools/exp/hostceil in this run; bytes of the whole job per step):
+def e2e_ceilings(hc, h2d, d2h_c, d2h_f, fill, staged, share):
+    """Seconds per step the host side needs AT LEAST -- for the compact path, the full-row path and the mix that was
+    timed (`share` of the rows as full rows) -- as the slowest of three resources (rates from tools/exp/hostceil in this
+    run; bytes of the whole job per step):
       pcie_h2d    x over PCIe, all GPUs concurrently
       dma_ingest  what the GPUs' copy engines write into host memory (F + compact G, or F + G), all GPUs concurrently
       host_dram   the bytes the step cannot avoid moving through host DRAM -- read by DMA (x), written by DMA, and for
-                  the compact path the rows stored by the expansion threads -- at the best TOTAL rate the tool saw on
-                  this box (non-temporal fill, memcpy read+write, or DMA + fill together).  The read-back of the
-                  staging blocks is left out: it can be served by the last-level cache (it is, on some boxes), so this
-                  is a true lower bound of the time; host_dram_with_staging_reads adds it."""
+                  compact rows the rows stored by the expansion threads -- at the best TOTAL rate the tool saw on this
+                  box (non-temporal fill, memcpy read+write, or DMA + fill together).  The read-back of the staging
+                  blocks is left out: it can be served by the last-level cache (it is, on some boxes), so this is a
+                  true lower bound of the time; host_dram_with_staging_reads adds it."""
     dram = max(hc["fill_nt_GBps"], hc["memcpy_rw_GBps"], hc["mix_d2h_GBps"] + hc["mix_fill_GBps"]) * 1e9
     out = {"dram_GBps": dram / 1e9,
            "model": "slowest of: x over PCIe; DMA ingest; unavoidable host-DRAM traffic (x read, DMA-written bytes, rows stored by "
                     "the threads; the staging read-back may hit the last-level cache and is listed separately) at the best total "
                     "rate the tool saw"}
-    for name, d2h, stores, back in (("compact_rows", d2h_c, fill, staged), ("full_rows", d2h_f, 0.0, 0.0)):
+    for name, p in (("compact_rows", 0.0), ("full_rows", 1.0), ("chosen", share)):
+        d2h, stores, back = p * d2h_f + (1 - p) * d2h_c, (1 - p) * fill, (1 - p) * staged
         parts = {"pcie_h2d": h2d / (hc["h2d_GBps"] * 1e9), "dma_ingest": d2h / (hc["d2h_GBps"] * 1e9),
                  "host_dram": (h2d + d2h + stores) / dram}
         ms = {k: 1e3 * v for k, v in parts.items()}
@@ -520,22 +522,33 @@ def run_ours(args, wl_name):
         t_, _ = e2e_run(1, full_copy)
         ok_ = close(Fh.numpy()[rows, :neF], Fr) and close(Gh.numpy()[rows, :neG], Gr)
         return reduce_max([t_])[0], ok_
-    (cal_c, ok_c), (cal_f, ok_f) = cal(False), cal(True)
+    cands = {}
+    cands[0], ok_c = cal(False)     # all chunks as compact rows
+    cands[100], ok_f = cal(True)    # all chunks as full rows
     ok = ok and ok_c and ok_f
-    use_full = cal_f < 0.95 * cal_c  # compact unless full rows are clearly faster on this box
-    ev.set_option("compact_host", 0 if use_full else 1)
-    t_e2e, e2e_launches = e2e_run(e2e_steps, False)  # the plain call: the context's option decides
+    # mixed: the copy engines carry a share of the chunks as full rows while the cores expand the others; the share that
+    # would equalise the two if they did not disturb each other, and half of it
+    p_star = int(round(100.0 * cands[0] / (cands[0] + cands[100])))
+    for pct in sorted({p_star, p_star // 2} - {0, 100}):
+        ev.set_option("full_rows_pct", pct)
+        cands[pct], ok_p = cal(False)
+        ok = ok and ok_p
+    best = min(cands, key=cands.get)
+    if cands[best] > 0.97 * cands[0]:
+        best = 0  # compact rows unless something else is clearly faster on this box
+    ev.set_option("compact_host", 0 if best == 100 else 1)
+    ev.set_option("full_rows_pct", 0 if best == 100 else best)
+    t_e2e, e2e_launches = e2e_run(e2e_steps, False)  # the plain call: the context's options decide
     ok = ok and close(Fh.numpy()[rows, :neF], Fr) and close(Gh.numpy()[rows, :neG], Gr)
-    other_steps = max(1, min(e2e_steps, 2))
     ev.set_option("compact_host", 1)
-    t_other, _ = e2e_run(other_steps, not use_full)
+    ev.set_option("full_rows_pct", 0)
     del Fh, Gh
     hc = None
     if rank == 0 and not args.no_ceiling:
         hc = host_ceiling(world, host_threads * world)
     barrier()
 
-    ms_dev, ms_serial, t_e2e, t_other, bad = reduce_max([ms_dev_local, ms_serial_local, t_e2e, t_other, 0.0 if ok else 1.0])
+    ms_dev, ms_serial, t_e2e, bad = reduce_max([ms_dev_local, ms_serial_local, t_e2e, 0.0 if ok else 1.0])
     per_rank_ms = gather_all(ms_dev_local / args.steps)
     rows_checked = int(sum(gather_all(float(rows.size))))
 
@@ -551,29 +564,33 @@ def run_ours(args, wl_name):
     clen = padded_ld(ev.compact_len)
     h2d, fill = 8.0 * n * B_total, 8.0 * neG * B_total
     d2h_c, d2h_f = 8.0 * (neF + clen) * B_total, 8.0 * (neF + neG) * B_total
-    api = {False: "G crosses PCIe as compact rows (x-dependent values only) and host threads write the rows in coordinate "
-                  "order, structural constants as literals",
-           True: "every G value crosses PCIe, straight into the caller's rows"}
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_f if use_full else d2h_c),
+    share = best / 100.0
+    what = ("every G value crosses PCIe, straight into the caller's rows" if best == 100 else
+            "G crosses PCIe as compact rows (x-dependent values only) and host threads write the rows in coordinate order, "
+            "structural constants as literals" + ("" if best == 0 else "; %d %% of the chunks cross as full rows instead, so "
+                                                  "that copy engines and cores work side by side" % best))
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(share * d2h_f + (1.0 - share) * d2h_c),
            "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps, "gpu_launches": e2e_launches,
            "api": "tolcuda_eval_batch(TOLCUDA_HOST_PTRS), pinned host x/F/G; full F and G rows in host memory at the end of "
-                  "every step; " + api[use_full],
-           "path": "full_rows" if use_full else "compact_rows",
-           "path_calibration": {"compact_rows_ms": 1e3 * cal_c, "full_rows_ms": 1e3 * cal_f,
-                                "rule": "one untimed step of each with all ranks active; full rows only if more than 5 % faster; "
-                                        "then tolcuda_set_option(compact_host)"},
+                  "every step; " + what,
+           "path": {"full_rows_pct": best, "compact_rows_pct": 100 - best},
+           "path_calibration": {"ms_per_step_by_full_rows_pct": {str(k): 1e3 * v for k, v in sorted(cands.items())},
+                                "rule": "one untimed step per candidate with all ranks active (all compact, all full, the share "
+                                        "t_c/(t_c+t_f) and half of it); the fastest, compact unless something is more than 3 % "
+                                        "faster; then tolcuda_set_option(compact_host / full_rows_pct)"},
            "host_threads_per_rank": host_threads,
-           "other_path": {"path": "compact_rows" if use_full else "full_rows", "value": units_step * other_steps / t_other,
-                          "unit": UNIT, "steps": other_steps, "ms_per_step": 1e3 * t_other / other_steps,
-                          "d2h_bytes_per_step": int(d2h_c if use_full else d2h_f), "api": api[not use_full]}}
+           "compact_rows_only": {"value": units_step / cands[0], "unit": UNIT, "ms_per_step": 1e3 * cands[0], "steps": 1},
+           "full_rows_only": {"value": units_step / cands[100], "unit": UNIT, "ms_per_step": 1e3 * cands[100], "steps": 1,
+                              "d2h_bytes_per_step": int(d2h_f)}}
     if hc:
-        c = e2e_ceilings(hc, h2d, d2h_c, d2h_f, fill, 8.0 * clen * B_total)
-        mine, other = ("full_rows", "compact_rows") if use_full else ("compact_rows", "full_rows")
-        e2e["ceiling"] = units_step / c[mine]["seconds"]
+        c = e2e_ceilings(hc, h2d, d2h_c, d2h_f, fill, 8.0 * clen * B_total, share)
+        e2e["ceiling"] = units_step / c["chosen"]["seconds"]
         e2e["frac"] = e2e_value / e2e["ceiling"]
-        e2e["ceiling_bound_by"] = c[mine]["bound_by"]
-        e2e["ceiling_ms"] = c[mine]["ms"]
-        e2e["other_path"]["ceiling"] = units_step / c[other]["seconds"]
+        e2e["ceiling_bound_by"] = c["chosen"]["bound_by"]
+        e2e["ceiling_ms"] = c["chosen"]["ms"]
+        e2e["compact_rows_only"]["ceiling"] = units_step / c["compact_rows"]["seconds"]
+        e2e["full_rows_only"]["ceiling"] = units_step / c["full_rows"]["seconds"]
         e2e["ceiling_source"] = {"tool": "tools/exp/hostceil (this run, this box)", **hc, "host_dram_GBps_used": c["dram_GBps"],
                                  "model": c["model"]}
     line = {

@@ -252,6 +252,10 @@ int tolcuda_set_host_threads(tolcuda_handle h, int threads);
  *                    host memory; 0: staged cudaMemcpyAsync copies
  *   "compact_host"   1 (default): the host-pointer batch path moves compact G rows across PCIe and expands them on
  *                    host threads; 0: full rows cross PCIe (as with TOLCUDA_FULL_G_COPY)
+ *   "full_rows_pct"  host-pointer batch path with compact_host = 1: this share of the chunks (0..100, default 0) crosses
+ *                    PCIe as full rows straight into the caller's G while the others go as compact rows and are
+ *                    expanded by the host threads -- the copy engines and the cores work side by side; the best share
+ *                    depends on the host (bench.py and tolbatch --host-path auto calibrate it)
  *   "chunk_mb"       host-pointer batch path: upper limit of the device megabytes per pipeline lane (default 32;
  *                    a call is cut into ~160 chunks of at least 1 MB, so smaller batches use smaller chunks)
  * Returns TOLCUDA_EINVAL for an unknown name or a value out of range. */

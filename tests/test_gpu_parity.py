@@ -193,6 +193,12 @@ def test_compact_rows_path_equals_full_rows(name, kernel, monkeypatch):
     ev.eval_batch_host(X, None, buf[:, 1:1 + ev.neG], needF=False)
     assert np.array_equal(buf[:, 1:1 + ev.neG].view(np.int64), Gf.view(np.int64))
     assert np.isnan(buf[:, 0]).all() and np.isnan(buf[:, 1 + ev.neG:]).all()
+    # mixed mode: a share of the chunks crosses PCIe as full rows, the others as compact rows -- same bits
+    for pct in (1, 30, 50, 99, 100):
+        ev.set_option("full_rows_pct", pct)
+        Fm, Gm = ev.eval_batch_host(X)
+        assert np.array_equal(Fm.view(np.int64), Ff.view(np.int64)) and np.array_equal(Gm.view(np.int64), Gf.view(np.int64)), pct
+    ev.set_option("full_rows_pct", 0)
     # caller-visible compact rows
     _, Gr = ev.eval_batch_host(X, compact_rows=True)
     assert Gr.shape == (B, T.evaluator.compact_len(m, ts))
@@ -362,7 +368,7 @@ def test_tolbatch_driver_end_to_end(tmp_path):
         for a, b in zip(sm["trajectories"], d["trajectories"]):
             assert a["objective"] == b["objective"] and a["max_abs_defect"] == b["max_abs_defect"]
         # --host-path full / auto: the same trajectories, bit for bit (the path only decides how G crosses PCIe)
-        for hp in ("full", "auto"):
+        for hp in ("full", "auto", "40"):
             js = str(tmp_path / ("hp_%s.json" % hp))
             r = subprocess.run([exe] + args + ["--root", root, "--batch", "300", "--steps", "1", "--json", js, "--host-path", hp],
                                capture_output=True, text=True, timeout=180)

@@ -352,7 +352,7 @@ def test_tolbatch_fails_loudly_on_bad_arguments_and_without_a_device():
         r = subprocess.run([exe] + pos + [opt, val], capture_output=True, text=True)
         assert r.returncode == 2 and msg in r.stderr and r.stdout == "", (opt, val, r.stderr)
     r = subprocess.run([exe] + pos + ["--host-path", "sideways"], capture_output=True, text=True)
-    assert r.returncode == 2 and "--host-path wants compact, full or auto" in r.stderr
+    assert r.returncode == 2 and "--host-path wants compact, full, auto or a percentage" in r.stderr
     r = subprocess.run([exe] + pos + ["--gather-gpu", "0", "--summary-only"], capture_output=True, text=True)
     assert r.returncode == 2 and "--gather-gpu" in r.stderr
     if not torch.cuda.is_available():

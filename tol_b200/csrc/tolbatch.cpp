@@ -14,15 +14,17 @@
 //                                             summary the kernels compute on the fly comes back
 //                                             (tolcuda_eval_batch_summary without F or G: objective, worst defect,
 //                                             worst boundary violation), no F/G rows on the host
-//            [--host-path compact|full|auto]  how G reaches the host rows: compact rows across PCIe + expansion by host
-//                                             threads (default), every G value across PCIe, or whichever of the two
-//                                             a calibration call of each finds faster on this box (the answer depends
+//            [--host-path compact|full|auto|P]  how G reaches the host rows: compact rows across PCIe + expansion by host
+//                                             threads (default), every G value across PCIe, P % of the chunks as full
+//                                             rows and the rest compact (copy engines and cores side by side), or
+//                                             whatever calibration calls find fastest on this box (the answer depends
 //                                             on the host: its DMA ingest rate against its cores' store rate)
 //            [--gather-gpu D]                 after the host gather: the same batch once more with every GPU's shard
 //                                             written straight into GPU D's memory by the shards' own kernels
 //                                             (tolcuda_gather_*: NVLink peer stores, no host in between), timed, and
 //                                             compared bit for bit with the rows of the host gather
 #include <chrono>
+#include <cctype>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -106,7 +108,9 @@ Args parse(int argc, char **argv) {
     if (a.nresults < 0) die("--nresults must not be negative");
     if (a.gpus < 0) die("--gpus must not be negative");
     if (a.ts < 0) die("--ts must not be negative");
-    if (a.host_path != "compact" && a.host_path != "full" && a.host_path != "auto") die("--host-path wants compact, full or auto");
+    if (a.host_path != "compact" && a.host_path != "full" && a.host_path != "auto" &&
+        !(std::isdigit((unsigned char)a.host_path[0]) && std::atoi(a.host_path.c_str()) <= 100))
+        die("--host-path wants compact, full, auto or a percentage 0..100");
     if (a.gather_gpu >= 0 && a.summary_only) die("--gather-gpu gathers F and G rows: not available with --summary-only");
     return a;
 }
@@ -166,17 +170,36 @@ int main(int argc, char **argv) {
     // evaluate: one host thread per device, contiguous block of trajectory indices each, no collective
     std::vector<double> secs(G, 0.0);
     double best = 1e300;
-    int path_flag = a.host_path == "full" ? TOLCUDA_FULL_G_COPY : 0;
-    double cal[2] = {0.0, 0.0};
-    // --host-path auto: two untimed calls of each path (the first one allocates), the faster second call wins
-    const int ncal = (a.host_path == "auto" && !a.summary_only) ? 4 : 0;
-    for (int step = -ncal; step < a.steps; step++) {
-        if (step < 0) path_flag = ((step + ncal) / 2) ? TOLCUDA_FULL_G_COPY : 0;
-        if (step == 0 && ncal) {
-            path_flag = cal[1] < 0.95 * cal[0] ? TOLCUDA_FULL_G_COPY : 0;
-            std::printf("TOLBATCH: host path calibration: compact rows %.3f ms, full rows %.3f ms -> %s\n", 1e3 * cal[0],
-                        1e3 * cal[1], path_flag ? "full rows" : "compact rows");
+    // share of the chunks that cross PCIe as full rows (tolcuda_set_option "full_rows_pct"; 100 = all of them)
+    auto set_share = [&](int pct) {
+        for (int g = 0; g < G; g++) {
+            check(tolcuda_set_option(h[g], "compact_host", pct == 100 ? 0 : 1), "tolcuda_set_option");
+            check(tolcuda_set_option(h[g], "full_rows_pct", pct == 100 ? 0 : pct), "tolcuda_set_option");
         }
+    };
+    int share = a.host_path == "full" ? 100 : (std::isdigit((unsigned char)a.host_path[0]) ? std::atoi(a.host_path.c_str()) : 0);
+    // --host-path auto: untimed calls (two per candidate, the first one allocates) of all compact, all full, then the
+    // share t_c / (t_c + t_f) that would balance copy engines and cores; the fastest wins, compact unless 3 % faster
+    std::vector<std::pair<int, double>> cal;
+    int ncal = (a.host_path == "auto" && !a.summary_only) ? 6 : 0;
+    for (int step = -ncal; step < a.steps; step++) {
+        if (step < 0) {
+            const int k = (step + ncal) / 2;
+            if (k == 0) share = 0;
+            else if (k == 1) share = 100;
+            else share = (int)std::lround(100.0 * cal[0].second / (cal[0].second + cal[1].second));
+        }
+        if (step == 0 && ncal) {
+            share = 0;
+            double tb = cal[0].second;
+            std::printf("TOLBATCH: host path calibration:");
+            for (auto &c : cal) {
+                std::printf(" %d %% full rows %.3f ms;", c.first, 1e3 * c.second);
+                if (c.second < 0.97 * cal[0].second && c.second < tb) tb = c.second, share = c.first;
+            }
+            std::printf(" -> %d %% full rows\n", share);
+        }
+        if (step <= 0) set_share(share);
         std::vector<std::thread> th;
         const auto t0 = std::chrono::steady_clock::now();
         for (int g = 0; g < G; g++)
@@ -189,14 +212,14 @@ int main(int argc, char **argv) {
                           "tolcuda_eval_batch_summary");
                 else if (b1 > b0)
                     check(tolcuda_eval_batch(h[g], b1 - b0, X + (size_t)b0 * ldx, ldx, F + (size_t)b0 * ldF, ldF,
-                                             Gv + (size_t)b0 * ldG, ldG, TOLCUDA_NEED_F | TOLCUDA_NEED_G | TOLCUDA_HOST_PTRS | path_flag),
+                                             Gv + (size_t)b0 * ldG, ldG, TOLCUDA_NEED_F | TOLCUDA_NEED_G | TOLCUDA_HOST_PTRS),
                           "tolcuda_eval_batch");
                 secs[g] = std::chrono::duration<double>(std::chrono::steady_clock::now() - s0).count();
             });
         for (auto &t : th) t.join();
         const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (step < 0) {
-            cal[(step + ncal) / 2] = wall;  // the second call of a path overwrites the first
+            if ((step + ncal) % 2) cal.emplace_back(share, wall);  // the second call of a candidate counts
             continue;
         }
         best = std::min(best, wall);

@@ -84,6 +84,8 @@ struct tolcuda_ctx {
     // host-pointer batch path
     BatchLane lane[NLANES];
     int compact_host = 1;  // host-pointer path: compact G across PCIe, expanded by host threads (0: full rows)
+    int full_rows_pct = 0;  // ... with this share of the chunks (0..100) sent as full rows all the same: the copy engines
+                            // carry them while the cores expand the others (what the host can take is box-dependent)
     int host_threads = 0;  // 0: HostPool::default_threads()
     std::unique_ptr<HostPool> pool;
     long launches = 0;
@@ -363,7 +365,7 @@ int tolcuda_create(const tolcuda_config *cfg, tolcuda_handle *out) {
     pattern_build(c.form, c.ts, h->iG, h->jG);
 
 #ifdef TOLCUDA_EXPERIMENTS
-    for (const char *name : {"kernel", "per", "per_min_waves", "tail_x4", "lwarps", "zero_copy", "compact_host", "chunk_mb"}) {
+    for (const char *name : {"kernel", "per", "per_min_waves", "tail_x4", "lwarps", "zero_copy", "compact_host", "chunk_mb", "full_rows_pct"}) {
         std::string env = std::string("TOLCUDA_") + name;
         for (char &ch : env) ch = (char)std::toupper((unsigned char)ch);
         if (env == "TOLCUDA_ZERO_COPY") env = "TOLCUDA_ZEROCOPY";
@@ -691,6 +693,13 @@ int tolcuda_eval_batch_summary(tolcuda_handle h, int B, const double *x, long ld
     const long dldx = tolcuda_padded_ld(c.n), dldF = tolcuda_padded_ld(c.neF);
     const long dldG = tolcuda_padded_ld(dev_compact ? lenGc : (long)c.neG);
     const long rowG = dev_compact ? lenGc : (long)c.neG;  // doubles of a G row that cross PCIe
+    // Mixed mode: a share of the chunks crosses PCIe as full rows (DMA straight into the caller's G) while the others
+    // go as compact rows and are expanded by the host threads -- the copy engines and the cores are different
+    // resources, and which of them a host has to spare differs from box to box.  Chunk ci is a
+    // full-row chunk when the running share crosses an integer (evenly spread over the call).
+    const int mix = via_compact ? h->full_rows_pct : 0;
+    const long dldGfull = tolcuda_padded_ld((long)c.neG);
+    auto full_chunk = [&](int ci) { return mix > 0 && ((long)(ci + 1) * mix) / 100 != ((long)ci * mix) / 100; };
     const size_t per_traj = sizeof(double) * (size_t)(dldx + dldF + dldG);
     // device bytes per lane: at most chunk_mb, and small enough for ~160 chunks per call (never below 1 MB) -- the
     // first chunk's copies and kernel and the last chunk's expansion are not overlapped with anything, which costs
@@ -704,7 +713,7 @@ int tolcuda_eval_batch_summary(tolcuda_handle h, int B, const double *x, long ld
     const int nchunks = (B + chunk - 1) / chunk;
     const int nlanes = std::min(NLANES, nchunks);
     for (int l = 0; l < nlanes; l++) {
-        int rc = ensure_lane(h, h->lane[l], chunk, dldG, via_compact ? dldG : 0);
+        int rc = ensure_lane(h, h->lane[l], chunk, mix > 0 ? dldGfull : dldG, via_compact ? dldG : 0);
         if (rc) return rc;
     }
     if (via_compact && !h->pool)
@@ -715,8 +724,9 @@ int tolcuda_eval_batch_summary(tolcuda_handle h, int B, const double *x, long ld
         const int b0 = ci * chunk, nb = std::min(chunk, B - b0);
         CU(cudaMemcpy2DAsync(l.d_x, sizeof(double) * dldx, x + (size_t)b0 * ldx, sizeof(double) * ldx,
                              sizeof(double) * c.n, nb, cudaMemcpyHostToDevice, l.stream));
-        int rc = launch(h, l.stream, nb, l.d_x, dldx, l.d_F, dldF, l.d_G, dldG, needF, needG,
-                        summary ? l.d_S : nullptr, 4, dev_compact);
+        const bool fullc = full_chunk(ci);
+        int rc = launch(h, l.stream, nb, l.d_x, dldx, l.d_F, dldF, l.d_G, fullc ? dldGfull : dldG, needF, needG,
+                        summary ? l.d_S : nullptr, 4, dev_compact && !fullc);
         if (rc) return rc;
         if (needF)
             CU(cudaMemcpy2DAsync(F + (size_t)b0 * ldF, sizeof(double) * ldF, l.d_F, sizeof(double) * dldF,
@@ -724,7 +734,10 @@ int tolcuda_eval_batch_summary(tolcuda_handle h, int B, const double *x, long ld
         if (summary)
             CU(cudaMemcpy2DAsync(summary + (size_t)b0 * lds, sizeof(double) * lds, l.d_S, sizeof(double) * 4,
                                  sizeof(double) * 4, nb, cudaMemcpyDeviceToHost, l.stream));
-        if (needG && via_compact)
+        if (needG && fullc)
+            CU(cudaMemcpy2DAsync(G + (size_t)b0 * ldG, sizeof(double) * ldG, l.d_G, sizeof(double) * dldGfull,
+                                 sizeof(double) * c.neG, nb, cudaMemcpyDeviceToHost, l.stream));
+        else if (needG && via_compact)
             CU(cudaMemcpyAsync(l.h_Gc, l.d_G, sizeof(double) * dldG * nb, cudaMemcpyDeviceToHost, l.stream));
         else if (needG)
             CU(cudaMemcpy2DAsync(G + (size_t)b0 * ldG, sizeof(double) * ldG, l.d_G, sizeof(double) * dldG,
@@ -744,7 +757,7 @@ int tolcuda_eval_batch_summary(tolcuda_handle h, int B, const double *x, long ld
             rc = cuda_fail(e, "cudaEventSynchronize");
             break;
         }
-        if (via_compact) {
+        if (via_compact && !full_chunk(ci)) {
             const int b0 = ci * chunk, nb = std::min(chunk, B - b0);
             expand_rows(*h->pool, c.form, c.ts, nb, l.h_Gc, dldG, G + (size_t)b0 * ldG, ldG);
         }
@@ -878,6 +891,7 @@ int tolcuda_set_option(tolcuda_handle h, const char *name, long value) {
     else if (k == "zero_copy") ok = in(0, 1), h->zero_copy = ok ? (int)value : h->zero_copy;
     else if (k == "compact_host") ok = in(0, 1), h->compact_host = ok ? (int)value : h->compact_host;
     else if (k == "chunk_mb") ok = in(1, 4096), h->chunk_mb = ok ? (int)value : h->chunk_mb;
+    else if (k == "full_rows_pct") ok = in(0, 100), h->full_rows_pct = ok ? (int)value : h->full_rows_pct;
     else {
         set_error("tolcuda_set_option: unknown option " + k);
         return TOLCUDA_EINVAL;
