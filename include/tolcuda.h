@@ -58,7 +58,13 @@ extern "C" {
  *                             F/G/summary may alias whatever that kernel read or wrote (e.g. the same F/G again)
  *   TOLCUDA_OVERLAP_DISJOINT  no wait at all: the caller also guarantees that F/G/summary overlap nothing the
  *                             preceding kernel reads or writes (e.g. consecutive chunks of a batch, or two sets
- *                             of result buffers used alternately) */
+ *                             of result buffers used alternately)
+ * What the hardware orders: a dependent grid may begin once every CTA of its predecessor has STARTED; nothing more.
+ * Launch i+2 can therefore only begin after every CTA of launch i+1 has started, i.e. after launch i+1 has worked
+ * off all but its last wave -- with two buffer sets used alternately, launch i+2 meets launch i only if a single CTA
+ * of launch i outlives (almost) all of launch i+1, which cannot happen once a launch is many CTA lifetimes long (a
+ * CTA lives ~10-20 us; from a few thousand trajectories per launch on).  A caller that needs the ordering
+ * unconditionally uses TOLCUDA_OVERLAP, or plain launches. */
 #define TOLCUDA_OVERLAP 0x200
 #define TOLCUDA_OVERLAP_DISJOINT 0x400
 #define TOLCUDA_FLAGS_ALL 0x7f3 /* every bit defined above; others are rejected with TOLCUDA_EINVAL */
