@@ -1101,8 +1101,14 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int nrun, int per_arg, const do
     const bool run = LOOP && bid < nrun;
     const size_t b0 = LOOP ? (run ? (size_t)per * bid : (size_t)per * nrun + (size_t)(bid - nrun)) : (size_t)bid;
     const int ntraj = run ? per : 1;
+#ifdef TOLCUDA_BALANCE  // experiment: the same number of windows for every warp instead of full tiles and a remainder
+    const int tw = (ts + nwarps - 1) / nwarps;
+    const int k0 = tw * warp;
+    const int nk = min(tw, ts - k0);
+#else
     const int k0 = 32 * warp;
     const int nk = min(32, ts - k0);
+#endif
     const int cnt = 1 + PX * (nk + 1);           // doubles of a slice
     const double *xw = x + b0 * ldx + (size_t)PX * k0;  // this warp's slice of the run's first trajectory
     slice_prefetch(wsm_s, xw, cnt, lane);
