@@ -94,3 +94,29 @@ def test_bench_reference_arm_prints_the_same_config_as_the_gpu_arm(oracle_built)
     assert line["e2e"] == {"value": line["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=60, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_bench_ceiling_is_the_slowest_resource():
+    """bench.py's e2e lower bound (host side of the box): per path the slowest of PCIe in, DMA ingest and unavoidable
+    host-DRAM traffic; the staging read-back only in the separate figure; full rows have no thread stores; a mix lies
+    between the two paths in DMA bytes"""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    B, n, neF, neG, clen = 65536, 2212, 1612, 21437, 6848
+    h2d, d2h_c, d2h_f, fill, staged = 8.0 * n * B, 8.0 * (neF + clen) * B, 8.0 * (neF + neG) * B, 8.0 * neG * B, 8.0 * clen * B
+    hc = {"d2h_GBps": 90.0, "h2d_GBps": 186.0, "fill_nt_GBps": 200.0, "memcpy_rw_GBps": 185.0, "mix_d2h_GBps": 52.0, "mix_fill_GBps": 52.0}
+    c = bench.e2e_ceilings(hc, h2d, d2h_c, d2h_f, fill, staged, 0.25)
+    assert c["dram_GBps"] == 200.0
+    cr, fr, mx = c["compact_rows"], c["full_rows"], c["chosen"]
+    assert cr["bound_by"] == "host_dram" and abs(cr["seconds"] - (h2d + d2h_c + fill) / 200e9) < 1e-12
+    assert abs(cr["ms"]["host_dram_with_staging_reads"] - 1e3 * (h2d + d2h_c + fill + staged) / 200e9) < 1e-9
+    assert fr["bound_by"] == "dma_ingest" and abs(fr["seconds"] - d2h_f / 90e9) < 1e-12 and "host_dram_with_staging_reads" not in fr["ms"]
+    assert cr["ms"]["dma_ingest"] < mx["ms"]["dma_ingest"] < fr["ms"]["dma_ingest"]
+    assert fr["ms"]["host_dram"] < mx["ms"]["host_dram"] < cr["ms"]["host_dram"]
+    # a host whose copy engines ingest faster than its cores store: full rows become the better bound
+    hc2 = dict(hc, d2h_GBps=175.0)
+    c2 = bench.e2e_ceilings(hc2, h2d, d2h_c, d2h_f, fill, staged, 0.0)
+    assert c2["full_rows"]["seconds"] < c2["compact_rows"]["seconds"]
+    assert bench.config_of("S10_tempest_ts200_B65536", 65536)["neG"] == neG
