@@ -91,9 +91,15 @@ constexpr int MODE_PLAIN = 0, MODE_SUMMARY = 1, MODE_COMPACT = 2;
 // matrix-free consumers of the Jacobian (G is never written): MODE_JVP  y = J(x) d  (the F pointer
 // receives y, the G pointer holds d), MODE_VJP  z = J(x)^T lambda  (the F pointer holds lambda, the G pointer receives z)
 constexpr int MODE_JVP = 3, MODE_VJP = 4;
+// F alone (needG == 0 in a plain call: SNOPT's line-search evaluations, screening): the same window arithmetic up to the
+// defects and nothing of the Jacobian's -- a third of the registers and no record slots, so three to four times the
+// warps per SM for what is a latency-bound chain (x slice -> 3 sincos -> defects -> staged F)
+constexpr int MODE_FONLY = 5;
 __host__ __device__ constexpr bool mode_is_op(int mode) { return mode == MODE_JVP || mode == MODE_VJP; }
 // the flavours that assemble whole records in the warp's record slots (the others use the tile as plain staging)
 __host__ __device__ constexpr bool mode_has_records(int mode) { return mode == MODE_PLAIN || mode == MODE_SUMMARY; }
+// doubles of a warp's tile in kernel A
+__host__ __device__ constexpr int tile_len_of(int mode) { return mode == MODE_FONLY ? 0 : TILE_LEN; }
 
 // Kernel experiment switches (bits 2.. of the kernels' needG argument: 4 = stage but do not store G, 8 = no
 // trigonometry, 16 = no Jacobian arithmetic) exist only in the experiments build (make exp -> libtolcuda_exp.so,
@@ -604,7 +610,7 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
         }
         __syncwarp();
     }
-    if (!needG) return;
+    if (MODE == MODE_FONLY || !needG) return;
 
     if (OP) {
     } else if (S10) {
@@ -1092,7 +1098,7 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int nrun, int per_arg, const do
     // hoists the address arithmetic the loop form has to re-derive per trajectory (7 % fewer instructions)
     const int per = LOOP ? per_arg : 1;
     const int nslice = per > 1 ? 2 : 1;  // slice buffers per warp (the host sizes the dynamic shared memory alike)
-    double *wsm = smem + (size_t)warp * (nslice * SX_LEN + TILE_LEN);
+    double *wsm = smem + (size_t)warp * (nslice * SX_LEN + tile_len_of(MODE));
     double *tile = wsm + nslice * SX_LEN;
     const uint32_t wsm_s = smem_addr(wsm), tile_s = wsm_s + 8 * nslice * SX_LEN;
     // CTAs [0, nrun) own runs of `per` consecutive trajectories, the CTAs behind them one trajectory each: the grid
@@ -1185,7 +1191,7 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int nrun, int per_arg, const do
             if (OP)
                 op_epilogue<FORM, MODE>(c, lane, dt, tT, n0, ne, Fb, Gb);
             else
-                traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG, dmax, dssq,
+                traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, MODE == MODE_FONLY ? 0 : needG, dmax, dssq,
                                     SUMM ? S + b * ldS : nullptr, MODE == MODE_COMPACT ? NVAR : REC);
         }
     }
@@ -1292,8 +1298,8 @@ fg_long_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, 
     if (OP)
         op_epilogue<FORM, MODE>(c, lane, dt, tT, n0, ne, Fb, Gb);
     else
-        traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, needG, dmax, dssq, SUMM ? S + b * ldS : nullptr,
-                            MODE == MODE_COMPACT ? NVAR : REC);
+        traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, MODE == MODE_FONLY ? 0 : needG, dmax, dssq,
+                            SUMM ? S + b * ldS : nullptr, MODE == MODE_COMPACT ? NVAR : REC);
 }
 
 // one launch, optionally as a programmatic dependent of the launch before it on the stream (FgLaunch::pdl)
@@ -1313,7 +1319,7 @@ template <int FORM, int WIND, int MAXT, int MINB, int MODE, bool LOOP>
 cudaError_t launch_cta_as(const FgLaunch &L, const int per, const int nsingle) {
     auto kern = fg_cta_kernel<FORM, WIND, MAXT, MINB, MODE, LOOP>;
     const int nthr = 32 * ((L.c->ts + 31) / 32);
-    const size_t smem = sizeof(double) * (size_t)(nthr / 32) * ((per > 1 ? 2 : 1) * SX_LEN + TILE_LEN);
+    const size_t smem = sizeof(double) * (size_t)(nthr / 32) * ((per > 1 ? 2 : 1) * SX_LEN + tile_len_of(MODE));
     // the attribute is per device (and this static per instantiation): tolbatch drives one device per thread
     static std::atomic<size_t> configured[MAX_DEVICES];
     std::atomic<size_t> &done = configured[L.device & (MAX_DEVICES - 1)];
@@ -1371,6 +1377,10 @@ cudaError_t launch_sel(const FgLaunch &L) {
     // and L.kernel == 2, take kernel L, whose warps walk several tiles each (any ts).
     const int ts = L.c->ts;
     if (L.kernel == 2 || ts > 256) return launch_long<FORM, WIND, MODE>(L);
+    if (MODE == MODE_FONLY) {  // 64 registers: 32 warps / SM at ts = 100, 28 at ts = 200
+        if (ts <= 128) return launch_cta<FORM, WIND, 128, 8, MODE>(L);
+        return launch_cta<FORM, WIND, 256, 4, MODE>(L);
+    }
     if (ts <= 128) return launch_cta<FORM, WIND, 128, 4, MODE>(L);                 // 128 registers, 16 warps / SM
     return launch_cta<FORM, WIND, 256, 2, MODE>(L);                          // 128 registers, 14-16 warps / SM
 }
@@ -1381,6 +1391,9 @@ cudaError_t launch_any(const FgLaunch &L) {
     if (L.op == 1) return launch_sel<FORM, WIND, MODE_JVP>(L);
     if (L.op == 2) return launch_sel<FORM, WIND, MODE_VJP>(L);
     if (L.compact) return launch_sel<FORM, WIND, MODE_COMPACT>(L);
+#ifndef TOLCUDA_NO_FONLY  // (variant builds measure the plain flavour on F-only calls)
+    if (!L.S && !L.needG && L.kernel != 2 && L.c->ts <= 256) return launch_sel<FORM, WIND, MODE_FONLY>(L);
+#endif
     return L.S ? launch_sel<FORM, WIND, MODE_SUMMARY>(L) : launch_sel<FORM, WIND, MODE_PLAIN>(L);
 }
 
