@@ -1373,16 +1373,18 @@ cudaError_t launch_long(const FgLaunch &L) {
 
 template <int FORM, int WIND, int MODE>
 cudaError_t launch_sel(const FgLaunch &L) {
-    // Kernel A needs the whole trajectory in one CTA with one tile per warp: ts <= 256.  Longer trajectories,
-    // and L.kernel == 2, take kernel L, whose warps walk several tiles each (any ts).
     const int ts = L.c->ts;
-    if (L.kernel == 2 || ts > 256) return launch_long<FORM, WIND, MODE>(L);
-    if (MODE == MODE_FONLY) {  // 64 registers: 32 warps / SM at ts = 100, 28 at ts = 200
+    if constexpr (MODE == MODE_FONLY) {
+        // kernel A only (launch_any sends ts <= 256 here).  64 registers: 32 warps / SM at ts <= 128, 28 at ts = 200
         if (ts <= 128) return launch_cta<FORM, WIND, 128, 8, MODE>(L);
         return launch_cta<FORM, WIND, 256, 4, MODE>(L);
+    } else {
+        // Kernel A needs the whole trajectory in one CTA with one tile per warp: ts <= 256.  Longer trajectories,
+        // and L.kernel == 2, take kernel L, whose warps walk several tiles each (any ts).
+        if (L.kernel == 2 || ts > 256) return launch_long<FORM, WIND, MODE>(L);
+        if (ts <= 128) return launch_cta<FORM, WIND, 128, 4, MODE>(L);             // 128 registers, 16 warps / SM
+        return launch_cta<FORM, WIND, 256, 2, MODE>(L);                          // 128 registers, 14-16 warps / SM
     }
-    if (ts <= 128) return launch_cta<FORM, WIND, 128, 4, MODE>(L);                 // 128 registers, 16 warps / SM
-    return launch_cta<FORM, WIND, 256, 2, MODE>(L);                          // 128 registers, 14-16 warps / SM
 }
 
 // the per-trajectory summary is a separate instantiation so that plain F/G launches pay nothing for it
