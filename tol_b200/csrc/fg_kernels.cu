@@ -95,11 +95,16 @@ constexpr int MODE_JVP = 3, MODE_VJP = 4;
 // defects and nothing of the Jacobian's -- a third of the registers and no record slots, so three to four times the
 // warps per SM for what is a latency-bound chain (x slice -> 3 sincos -> defects -> staged F)
 constexpr int MODE_FONLY = 5;
+// ... and the same with the per-trajectory summary (screening: x in, [objective, worst defect, worst boundary violation,
+// sum of defect^2] out, F optional)
+constexpr int MODE_FSUMM = 6;
+__host__ __device__ constexpr bool mode_is_fonly(int mode) { return mode == MODE_FONLY || mode == MODE_FSUMM; }
+__host__ __device__ constexpr bool mode_has_summary(int mode) { return mode == 1 || mode == MODE_FSUMM; }
 __host__ __device__ constexpr bool mode_is_op(int mode) { return mode == MODE_JVP || mode == MODE_VJP; }
 // the flavours that assemble whole records in the warp's record slots (the others use the tile as plain staging)
 __host__ __device__ constexpr bool mode_has_records(int mode) { return mode == MODE_PLAIN || mode == MODE_SUMMARY; }
 // doubles of a warp's tile in kernel A
-__host__ __device__ constexpr int tile_len_of(int mode) { return mode == MODE_FONLY ? 0 : TILE_LEN; }
+__host__ __device__ constexpr int tile_len_of(int mode) { return mode_is_fonly(mode) ? 0 : TILE_LEN; }
 
 // Kernel experiment switches (bits 2.. of the kernels' needG argument: 4 = stage but do not store G, 8 = no
 // trigonometry, 16 = no Jacobian arithmetic) exist only in the experiments build (make exp -> libtolcuda_exp.so,
@@ -581,7 +586,7 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
         f[7] = s1[7] - dCL * dt - s0[7];
     }
     ts_out.dmax = 0.0, ts_out.dssq = 0.0;
-    if (MODE == MODE_SUMMARY) {
+    if (mode_has_summary(MODE)) {
         double m = 0.0, q = 0.0;
         if (active) {
 #pragma unroll
@@ -610,7 +615,7 @@ __device__ __forceinline__ void tile_eval(const FgConst &c, double *sx, double *
         }
         __syncwarp();
     }
-    if (MODE == MODE_FONLY || !needG) return;
+    if (mode_is_fonly(MODE) || !needG) return;
 
     if (OP) {
     } else if (S10) {
@@ -1084,7 +1089,7 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int nrun, int per_arg, const do
                double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG, int flow,
                double *__restrict__ S, long ldS) {
     pdl_release();
-    constexpr bool SUMM = (MODE == MODE_SUMMARY);
+    constexpr bool SUMM = mode_has_summary(MODE);
     extern __shared__ __align__(16) double smem[];
     constexpr bool OP = mode_is_op(MODE);
     __shared__ double red[MAXPER][SUMM ? 4 : 2][32];
@@ -1191,7 +1196,7 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int nrun, int per_arg, const do
             if (OP)
                 op_epilogue<FORM, MODE>(c, lane, dt, tT, n0, ne, Fb, Gb);
             else
-                traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, MODE == MODE_FONLY ? 0 : needG, dmax, dssq,
+                traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, mode_is_fonly(MODE) ? 0 : needG, dmax, dssq,
                                     SUMM ? S + b * ldS : nullptr, MODE == MODE_COMPACT ? NVAR : REC);
         }
     }
@@ -1213,7 +1218,7 @@ fg_long_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, 
                double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG, int flow,
                double *__restrict__ S, long ldS) {
     pdl_release();
-    constexpr bool SUMM = (MODE == MODE_SUMMARY);
+    constexpr bool SUMM = mode_has_summary(MODE);
     extern __shared__ __align__(16) double smem[];
     constexpr bool OP = mode_is_op(MODE);
     __shared__ double red[SUMM ? 4 : 2][32];
@@ -1298,7 +1303,7 @@ fg_long_kernel(const __grid_constant__ FgConst c, const double *__restrict__ x, 
     if (OP)
         op_epilogue<FORM, MODE>(c, lane, dt, tT, n0, ne, Fb, Gb);
     else
-        traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, MODE == MODE_FONLY ? 0 : needG, dmax, dssq,
+        traj_epilogue<FORM>(c, lane, dt, tT, tp, n0, ne, Fb, Gb, needF, mode_is_fonly(MODE) ? 0 : needG, dmax, dssq,
                             SUMM ? S + b * ldS : nullptr, MODE == MODE_COMPACT ? NVAR : REC);
 }
 
@@ -1374,7 +1379,7 @@ cudaError_t launch_long(const FgLaunch &L) {
 template <int FORM, int WIND, int MODE>
 cudaError_t launch_sel(const FgLaunch &L) {
     const int ts = L.c->ts;
-    if constexpr (MODE == MODE_FONLY) {
+    if constexpr (mode_is_fonly(MODE)) {
         // kernel A only (launch_any sends ts <= 256 here).  64 registers: 32 warps / SM at ts <= 128, 28 at ts = 200
         if (ts <= 128) return launch_cta<FORM, WIND, 128, 8, MODE>(L);
         return launch_cta<FORM, WIND, 256, 4, MODE>(L);
@@ -1394,7 +1399,8 @@ cudaError_t launch_any(const FgLaunch &L) {
     if (L.op == 2) return launch_sel<FORM, WIND, MODE_VJP>(L);
     if (L.compact) return launch_sel<FORM, WIND, MODE_COMPACT>(L);
 #ifndef TOLCUDA_NO_FONLY  // (variant builds measure the plain flavour on F-only calls)
-    if (!L.S && !L.needG && L.kernel != 2 && L.c->ts <= 256) return launch_sel<FORM, WIND, MODE_FONLY>(L);
+    if (!L.needG && L.kernel != 2 && L.c->ts <= 256)
+        return L.S ? launch_sel<FORM, WIND, MODE_FSUMM>(L) : launch_sel<FORM, WIND, MODE_FONLY>(L);
 #endif
     return L.S ? launch_sel<FORM, WIND, MODE_SUMMARY>(L) : launch_sel<FORM, WIND, MODE_PLAIN>(L);
 }

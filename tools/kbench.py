@@ -75,7 +75,23 @@ with torch.cuda.stream(st):
     e1.record(st)
     torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / args.steps
-by = 8.0 * B * (n + (neF if needF else 0) + (neG if needG else 0))
+if args.need == "S":  # screening: only the per-trajectory summary is produced (tolcuda_eval_batch_summary, F = G = NULL)
+    Sd = torch.empty(B, 4, dtype=torch.float64, device="cuda")
+    fl = T.evaluator.DEVICE_PTRS | T.evaluator.NO_SYNC
+    def summ():
+        T.lib.check(ev.L.tolcuda_eval_batch_summary(ev.h, B, Xd.data_ptr(), Xd.stride(0), None, 0, None, 0, Sd.data_ptr(), 4, fl))
+    with torch.cuda.stream(st):
+        for _ in range(args.warmup):
+            summ()
+        torch.cuda.synchronize()
+        e0.record(st)
+        for _ in range(args.steps):
+            summ()
+        e1.record(st)
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    needF = needG = False
+by = 8.0 * B * (n + (neF if needF else 0) + (neG if needG else 0) + (4 if args.need == "S" else 0))
 print(json.dumps({"workload": args.workload, "B": B, "kernel": args.kernel, "per": args.per, "tail_x4": args.tail_x4, "overlap": args.overlap, "goff": args.goff, "need": args.need, "ms": ms,
                   "node_evals_per_s": B * ts / (ms * 1e-3), "GBps": by / ms / 1e6,
                   "frac_of_6544": by / ms / 1e6 / 6544.0}))
