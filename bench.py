@@ -779,6 +779,52 @@ def secondary_records(torch, T, stream, peak):
     ev.close()
     del X, outs
 
+    # F alone (needG = 0: SNOPT's line-search evaluations) and the summary alone (screening) on the bench's own batch:
+    # the 64-register flavours of the kernel (MODE_FONLY / MODE_FSUMM)
+    fixture, seed0, B = WORKLOADS["S10_tempest_ts200_B65536"]
+    g = golden(fixture)
+    ev = T.Evaluator.from_golden(g)
+    ev.set_stream(stream.cuda_stream)
+    ts = int(g["ts"])
+    ldx, ldF = padded_ld(ev.n), padded_ld(ev.neF)
+    U = 2048  # distinct rows, tiled (timing only; F of the first rows is checked against the oracle port)
+    Xu = torch.zeros(U, ldx, dtype=torch.float64)
+    T.synth.batch(g["x"][0], seed0, 0, U, out=Xu.numpy())
+    X = Xu.cuda()[torch.arange(B, device="cuda") % U].contiguous()
+    Fd = torch.empty(B, ldF, dtype=torch.float64, device="cuda")
+    Sd = torch.empty(B, 4, dtype=torch.float64, device="cuda")
+    Gnone = torch.empty(0, 1, dtype=torch.float64, device="cuda")
+    fl = T.evaluator.DEVICE_PTRS | T.evaluator.NO_SYNC
+
+    def f_only():
+        ev.eval_batch_device(X, Fd, Gnone, needF=True, needG=False, sync=False)
+
+    def s_only():
+        T.lib.check(ev.L.tolcuda_eval_batch_summary(ev.h, B, X.data_ptr(), X.stride(0), None, 0, None, 0, Sd.data_ptr(), 4, fl))
+    for key, fn, by in (("f_only", f_only, 8.0 * (ev.n + ev.neF) * B), ("summary_only", s_only, 8.0 * (ev.n + 4) * B)):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        steps = 100
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        sec[key] = {"workload": "S10_tempest_ts200_B65536", "launch_ms": ms, "value": B * ts / (ms * 1e-3), "unit": UNIT,
+                    "bytes_per_launch": by, "GBps": by / ms / 1e6, "frac_of_own_bytes": by / ms / 1e6 / peak, "steps": steps}
+    port = P.PortProblem(str(g["mission"]), ts, g["ac"], g["gn"], g["goal_ned"], int(g["wind_model"]))
+    Fr, Gr = np.empty((8, ev.neF)), np.empty((8, ev.neG))
+    port.eval_many(np.ascontiguousarray(Xu.numpy()[:8, :ev.n]), Fr, Gr)
+    Sh = Sd[:8].cpu().numpy()
+    sec["f_only"]["parity_spot_check"] = close(Fd[:8, :ev.neF].cpu().numpy(), Fr)
+    sec["summary_only"]["parity_spot_check"] = bool(close(Sh[:, 0], Fr[:, 0]) and
+                                                    close(Sh[:, 1], np.abs(Fr[:, 1:1 + 8 * ts]).max(axis=1)))
+    ev.close()
+    del X, Fd, Sd
+
     # DEFINEGusrfg_ exactly as SNOPT calls it, on the reference's own initial guess; timed from Python through ctypes
     # with pre-built argument objects (about a microsecond of marshalling per call is included)
     cb = {}
