@@ -722,6 +722,45 @@ def test_launch_shapes_and_overlapped_launches_give_the_same_bits(name):
     ev.close()
 
 
+@pytest.mark.parametrize("name", ["S10_tempest_ts100", "G7_tempestwences_ts45_gains", "S10_tempest_ts200"])
+def test_every_execution_option_gives_the_same_bits(name):
+    """tolcuda_set_option (include/tolcuda.h): every option chooses between equivalent ways of running the same
+    arithmetic.  The single-trajectory callback (zero-copy kernel on mapped pinned memory / staged copies, compact or
+    full G row across PCIe), the tile-loop kernel with every warp count, the host-pointer batch path with any chunk
+    size and any share of full-row chunks: all bit for bit the default's F and G."""
+    g = load_golden(name)
+    ev = T.Evaluator.from_golden(g)
+    x = g["x"][1]
+    F0, G0 = ev.eval(x)
+    B = 61
+    X = T.synth.batch(g["x"][0], 97, 0, B)
+    Fb0, Gb0 = ev.eval_batch_host(X)
+    for opt, values, restore in (("zero_copy", (0, 1), 1), ("compact_host", (0, 1), 1)):
+        for v in values:
+            ev.set_option(opt, v)
+            for needF, needG in ((1, 1), (1, 0), (0, 1)):
+                st, F, G = ev.usrfun(x, needF, needG)
+                assert st == 0
+                assert (not needF) or np.array_equal(F.view(np.int64), F0.view(np.int64)), (opt, v)
+                assert (not needG) or np.array_equal(G.view(np.int64), G0.view(np.int64)), (opt, v)
+            Fb, Gb = ev.eval_batch_host(X)
+            assert np.array_equal(Fb.view(np.int64), Fb0.view(np.int64)) and np.array_equal(Gb.view(np.int64), Gb0.view(np.int64)), (opt, v)
+        ev.set_option(opt, restore)
+    ev.set_option("kernel", 2)
+    for w in range(0, 9):
+        ev.set_option("lwarps", w)
+        Fb, Gb = ev.eval_batch_host(X, full_copy=True)
+        assert np.array_equal(Fb.view(np.int64), Fb0.view(np.int64)) and np.array_equal(Gb.view(np.int64), Gb0.view(np.int64)), ("lwarps", w)
+    ev.set_option("lwarps", 0)
+    ev.set_option("kernel", 0)
+    for mb, pct in ((1, 0), (1, 37), (2, 100), (64, 50), (4096, 0)):
+        ev.set_option("chunk_mb", mb)
+        ev.set_option("full_rows_pct", pct)
+        Fb, Gb = ev.eval_batch_host(X)
+        assert np.array_equal(Fb.view(np.int64), Fb0.view(np.int64)) and np.array_equal(Gb.view(np.int64), Gb0.view(np.int64)), (mb, pct)
+    ev.close()
+
+
 def test_api_misuse_is_reported_not_executed():
     """error behaviour of the C ABI on a live device: bad arguments come back as TOLCUDA_E* codes with a
     message, nothing is written, and the callback turns a mismatching problem size into Status = -2"""
