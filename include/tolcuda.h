@@ -245,8 +245,10 @@ int tolcuda_jac_tvec(tolcuda_handle h, int B, const double *x, long ldx, const d
  * environment TOLCUDA_HOST_THREADS, else the cores available to the process / LOCAL_WORLD_SIZE) */
 int tolcuda_set_host_threads(tolcuda_handle h, int threads);
 
-/* Execution-strategy options of a context.  EVERY value of EVERY option yields the same bits in F and G (tested);
- * they choose between equivalent ways of running the same arithmetic:
+/* Execution-strategy options of a context.  They choose between equivalent ways of running the same arithmetic:
+ * every value of every option yields the same bits in F and G (tested), with one exception -- the tile-loop kernel
+ * ("kernel" = 2, always used for ts > 256) adds the terms of the objective per lane over a warp's tiles first, so
+ * F[0], and only F[0], can differ from the default kernel's in the last bits (and with "lwarps"):
  *   "kernel"         0 (default): one CTA per run of trajectories for ts <= 256, the tile-loop kernel beyond;
  *                    2: the tile-loop kernel for any ts
  *   "per"            trajectories per CTA, 1..4; 0 (default) = 2 for large batches, 1 below "per_min_waves" waves
