@@ -258,9 +258,6 @@ int tolcuda_set_host_threads(tolcuda_handle h, int threads);
  *   "lwarps"         warps per CTA of the tile-loop kernel, 1..8; 0 (default) = the count that balances the tiles
  *   "zero_copy"      1 (default): the single-trajectory path lets the kernel read x / write F, G in mapped pinned
  *                    host memory; 0: staged cudaMemcpyAsync copies
- *   "poll_flag"      1 (default): with zero_copy, the single-trajectory kernel (ts <= 256) ends by writing a completion
- *                    word into that pinned block after all of its stores have landed and the host spins on it; 0: the
- *                    host synchronises the stream
  *   "compact_host"   1 (default): the host-pointer batch path moves compact G rows across PCIe and expands them on
  *                    host threads; 0: full rows cross PCIe (as with TOLCUDA_FULL_G_COPY)
  *   "full_rows_pct"  host-pointer batch path with compact_host = 1: this share of the chunks (0..100, default 0) crosses

@@ -736,7 +736,7 @@ def test_every_execution_option_gives_the_same_bits(name):
     B = 61
     X = T.synth.batch(g["x"][0], 97, 0, B)
     Fb0, Gb0 = ev.eval_batch_host(X)
-    for opt, values, restore in (("zero_copy", (0, 1), 1), ("compact_host", (0, 1), 1), ("poll_flag", (0, 1), 1)):
+    for opt, values, restore in (("zero_copy", (0, 1), 1), ("compact_host", (0, 1), 1)):
         for v in values:
             ev.set_option(opt, v)
             for needF, needG in ((1, 1), (1, 0), (0, 1)):

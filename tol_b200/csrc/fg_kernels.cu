@@ -1087,7 +1087,7 @@ template <int FORM, int WIND, int MAXT, int MINB, int MODE, bool LOOP>
 __global__ void __launch_bounds__(MAXT, MINB)
 fg_cta_kernel(const __grid_constant__ FgConst c, int nrun, int per_arg, const double *__restrict__ x, long ldx,
                double *__restrict__ F, long ldF, double *__restrict__ G, long ldG, int needF, int needG, int flow,
-               double *__restrict__ S, long ldS, unsigned *done_flag, unsigned done_value) {
+               double *__restrict__ S, long ldS) {
     pdl_release();
     constexpr bool SUMM = mode_has_summary(MODE);
     extern __shared__ __align__(16) double smem[];
@@ -1201,19 +1201,6 @@ fg_cta_kernel(const __grid_constant__ FgConst c, int nrun, int per_arg, const do
         }
     }
     cp_async_wait<0>();
-    if (done_flag) {
-        // Single-trajectory callback (one CTA): the host polls this word instead of synchronising the stream.  First
-        // every warp's own stores -- its bulk copies COMPLETE (not merely read), then everything visible system-wide:
-        // the outputs live in mapped host memory --, then the block barrier, then the flag.
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        __syncwarp();
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence_system();
-            *reinterpret_cast<volatile unsigned *>(done_flag) = done_value;
-        }
-    }
 }
 
 // ---- kernel L: one CTA per trajectory of any length -------------------------------------------------------------
@@ -1349,7 +1336,7 @@ cudaError_t launch_cta_as(const FgLaunch &L, const int per, const int nsingle) {
     const int nrun = LOOP ? (L.B - nsingle) / per : 0;  // nsingle makes this exact (launch_cta)
     const int grid = LOOP ? nrun + nsingle : L.B;
     return launch_kernel(kern, grid, nthr, smem, L, *L.c, nrun, per, L.x, L.ldx, L.F, L.ldF, L.G, L.ldG, L.needF, L.needG,
-                         L.pdl == 1 ? FLOW_WAIT : 0, L.S, L.ldS, grid == 1 ? L.done_flag : nullptr, L.done_value);
+                         L.pdl == 1 ? FLOW_WAIT : 0, L.S, L.ldS);
 }
 
 // Runs of `per` trajectories per CTA pay off once the grid is many waves deep (the x load and the CTA launch

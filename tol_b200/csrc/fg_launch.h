@@ -32,8 +32,6 @@ struct FgLaunch {
     int pdl;       // 0: ordinary launch; 1: programmatic dependent launch, the kernel waits for the preceding launch on
                    // the stream before its first store; 2: the same without the wait (outputs disjoint from the
                    // preceding launch's reads and writes).  Never set for op != 0 (d / lambda are read early).
-    unsigned *done_flag;  // kernel A, single-CTA launches: word (mapped host memory) that receives done_value after every
-    unsigned done_value;  // store of the launch has landed -- the host polls it instead of synchronising the stream
     int sm_count;  // SMs of the device
     int device;    // CUDA device ordinal the launch goes to (the current device)
     cudaStream_t stream;

@@ -73,10 +73,6 @@ struct tolcuda_ctx {
                              // TOLCUDA_OVERLAP_DISJOINT launches (the next grid fills the tail anyway)
     int lwarps = 0;  // kernel L: warps per CTA override (0 = automatic)
     int zero_copy = 1;  // single-trajectory path: kernel works on the mapped pinned block (0: staged copies)
-    int poll_flag = 1;  // ... and tells the host through a word in that block that its stores have landed (0: the host
-                        // synchronises the stream instead)
-    unsigned epoch = 0; // value of the last launch's completion word
-    long oflag = 0;     // offset (doubles) of that word in h_one
     int chunk_mb = 32;  // host-pointer path: device bytes per lane (measured: 8..64 MB equally good, tools/expandbw.py)
     int sm_count = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -108,7 +104,7 @@ long round_up(long v, long m) { return (v + m - 1) / m * m; }
 
 int launch(tolcuda_ctx *h, cudaStream_t st, int B, const double *x, long ldx, double *F, long ldF,
            double *G, long ldG, int needF, int needG, double *S = nullptr, long ldS = 0, int compact = 0, int op = 0,
-           int pdl = 0, unsigned *done_flag = nullptr, unsigned done_value = 0) {
+           int pdl = 0) {
     FgLaunch L{};
     L.S = S, L.ldS = ldS;
     L.compact = compact;
@@ -122,7 +118,6 @@ int launch(tolcuda_ctx *h, cudaStream_t st, int B, const double *x, long ldx, do
     L.lwarps = h->lwarps;
     L.per_auto = h->per_auto;
     L.pdl = op ? 0 : pdl;
-    L.done_flag = done_flag, L.done_value = done_value;
     L.per_min_waves = h->per_min_waves >= 0 ? h->per_min_waves : (L.pdl == 2 ? 8 : 24);
     L.tail_waves_x4 = h->tail_waves_x4 >= 0 ? h->tail_waves_x4 : (L.pdl == 2 ? 0 : 2);
     L.sm_count = h->sm_count;
@@ -370,7 +365,7 @@ int tolcuda_create(const tolcuda_config *cfg, tolcuda_handle *out) {
     pattern_build(c.form, c.ts, h->iG, h->jG);
 
 #ifdef TOLCUDA_EXPERIMENTS
-    for (const char *name : {"kernel", "per", "per_min_waves", "tail_x4", "lwarps", "zero_copy", "poll_flag", "compact_host", "chunk_mb", "full_rows_pct"}) {
+    for (const char *name : {"kernel", "per", "per_min_waves", "tail_x4", "lwarps", "zero_copy", "compact_host", "chunk_mb", "full_rows_pct"}) {
         std::string env = std::string("TOLCUDA_") + name;
         for (char &ch : env) ch = (char)std::toupper((unsigned char)ch);
         if (env == "TOLCUDA_ZERO_COPY") env = "TOLCUDA_ZEROCOPY";
@@ -394,11 +389,9 @@ int tolcuda_create(const tolcuda_config *cfg, tolcuda_handle *out) {
         h->ox = 0;
         h->oF = tolcuda_padded_ld(c.n);
         h->oG = h->oF + tolcuda_padded_ld(c.neF);
-        h->oflag = h->oG + tolcuda_padded_ld(c.neG);
-        const size_t bytes = sizeof(double) * (h->oflag + 16);
+        const size_t bytes = sizeof(double) * (h->oG + tolcuda_padded_ld(c.neG));
         e = cudaMallocHost(&h->h_one, bytes);
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMallocHost"); break; }
-        std::memset(h->h_one + h->oflag, 0, sizeof(double) * 16);
         e = cudaMalloc(&h->d_one, bytes);
         if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMalloc"); break; }
     } while (0);
@@ -610,30 +603,10 @@ int tolcuda_eval(tolcuda_handle h, const double *x, int needF, double *F, int ne
     if (h->zero_copy) {
         // One launch, no copy commands: the pinned staging block is mapped into the device's address
         // space (UVA), so the kernel reads x from it and writes F/G into it across PCIe directly.
-        // Completion: kernel A (ts <= 256) ends by writing the call's epoch into a word of the same pinned block once
-        // all of its stores have landed; the host spins on that word -- no stream synchronisation, whose wake-up costs
-        // more than the kernel.  A failed launch or kernel is caught by querying the stream every few thousand spins.
-        const bool poll = h->poll_flag && h->kernel != 2 && c.ts <= 256;
-        volatile unsigned *flag = reinterpret_cast<volatile unsigned *>(h->h_one + h->oflag);
-        const unsigned epoch = ++h->epoch;
         int rc = launch(h, st, 1, h->h_one + h->ox, c.n, h->h_one + h->oF, c.neF, h->h_one + h->oG, lenG,
-                        needF > 0, needG > 0, nullptr, 0, compact, 0, 0, poll ? const_cast<unsigned *>(flag) : nullptr, epoch);
+                        needF > 0, needG > 0, nullptr, 0, compact);
         if (rc) return rc;
-        if (poll) {
-            for (unsigned spins = 0; *flag != epoch; spins++) {
-                if ((spins & 0xfff) == 0xfff) {
-                    cudaError_t q = cudaStreamQuery(st);
-                    if (q == cudaSuccess) break;  // finished: the word is written before the kernel ends
-                    if (q != cudaErrorNotReady) return cuda_fail(q, "single-trajectory kernel");
-                }
-#if defined(__x86_64__) || defined(__i386__)
-                __builtin_ia32_pause();
-#endif
-            }
-            std::atomic_thread_fence(std::memory_order_acquire);
-        } else {
-            CU(cudaStreamSynchronize(st));
-        }
+        CU(cudaStreamSynchronize(st));
     } else {
         CU(cudaMemcpyAsync(h->d_one + h->ox, h->h_one + h->ox, sizeof(double) * c.n, cudaMemcpyHostToDevice, st));
         int rc = launch(h, st, 1, h->d_one + h->ox, c.n, h->d_one + h->oF, c.neF, h->d_one + h->oG, lenG,
@@ -916,7 +889,6 @@ int tolcuda_set_option(tolcuda_handle h, const char *name, long value) {
     else if (k == "tail_x4") ok = in(-1, 64), h->tail_waves_x4 = ok ? (int)value : h->tail_waves_x4;
     else if (k == "lwarps") ok = in(0, 8), h->lwarps = ok ? (int)value : h->lwarps;
     else if (k == "zero_copy") ok = in(0, 1), h->zero_copy = ok ? (int)value : h->zero_copy;
-    else if (k == "poll_flag") ok = in(0, 1), h->poll_flag = ok ? (int)value : h->poll_flag;
     else if (k == "compact_host") ok = in(0, 1), h->compact_host = ok ? (int)value : h->compact_host;
     else if (k == "chunk_mb") ok = in(1, 4096), h->chunk_mb = ok ? (int)value : h->chunk_mb;
     else if (k == "full_rows_pct") ok = in(0, 100), h->full_rows_pct = ok ? (int)value : h->full_rows_pct;

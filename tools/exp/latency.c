@@ -28,7 +28,6 @@ int main(int argc, char **argv) {
     tolcuda_get_config(h, &cfg);
     double *x = malloc(8 * n), *F = malloc(8 * neF), *G = malloc(8 * neG);
     tolcuda_problem_initial_guess(&cfg, x);
-    if (getenv("TOLCUDA_LATENCY_POLL")) tolcuda_set_option(h, "poll_flag", atoi(getenv("TOLCUDA_LATENCY_POLL")));
     tolcuda_bind_global(h);
     int status = 0, zero = 0;
     const char *lab[3] = {"F+G", "F", "G"};
